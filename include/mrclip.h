@@ -1,0 +1,110 @@
+/*
+ * mrclip.h — C ABI of the B200-native contrastive-loss hot path.
+ *
+ * This is the drop-in boundary for MR-CLIP's distributed contrastive loss
+ * (reference: src/open_clip/loss.py).  Plain pointers and sizes only; every
+ * pointer is a CUDA device pointer unless stated otherwise; `stream` is a
+ * cudaStream_t passed as void*.  Every entry returns 0 on success, a positive
+ * cudaError_t on a CUDA failure, a negative value on an argument / driver-API
+ * error; mrclip_last_error() returns the message (thread local).  Nothing here
+ * synchronises the device, allocates device memory or touches Python.
+ *
+ * Conventions
+ *   - Feature matrices handed to the kernels are bf16, row-major, with leading
+ *     dimension `ld = mrclip_padded_dim(d)` (zero padded); mrclip_pack_bf16
+ *     produces them from fp32 / bf16 / fp16 inputs.
+ *   - "lse2" vectors are log-sum-exp values in log2 units (lse_natural * log2(e)).
+ *   - A "row pass" contracts this rank's m_rows rows (A) against all n_cols rows
+ *     of the other modality (B).  label_offset is the global column index of
+ *     row 0's positive (= rank * m_rows), reference loss.py:94-96.
+ */
+#ifndef MRCLIP_H_
+#define MRCLIP_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MRCLIP_DT_F32 0
+#define MRCLIP_DT_BF16 1
+#define MRCLIP_DT_F16 2
+
+typedef struct mrclip_shape {
+  int m_rows;       /* rows owned by this rank (n) */
+  int n_cols;       /* rows of the gathered other modality (N = world_size * n) */
+  int d;            /* embedding dimension */
+  int label_offset; /* global column of local row 0's positive */
+} mrclip_shape;
+
+/* library / build identification; mrclip_version() = 10000*major + 100*minor + patch */
+int mrclip_version(void);
+const char* mrclip_last_error(void);
+/* 1 when a CUDA device of compute capability 10.x is present, else 0 (no compute is attempted). */
+int mrclip_device_ok(void);
+
+/* leading dimension of packed bf16 rows (d rounded up to 8) and of [*, N] buffers (N rounded to 128) */
+int mrclip_padded_dim(int d);
+int mrclip_padded_cols(int n_cols);
+/* scratch bytes needed by any fwd/bwd entry for this shape (caller allocates, 256 B aligned) */
+size_t mrclip_workspace_bytes(int m_rows, int n_cols, int d);
+/* column ranges given to mrclip_clip_fwd_tiles must start on a multiple of this many columns */
+int mrclip_fwd_col_granule(int m_rows, int n_cols);
+
+/* src [rows, d] of dtype MRCLIP_DT_* with leading dim src_ld  ->  dst bf16 [rows, dst_ld] (zero padded).
+ * Replaces the implicit autocast casts in front of loss.py:117-124. */
+int mrclip_pack_bf16(const void* src, int src_dtype, int rows, int d, long src_ld, void* dst,
+                     int dst_ld, void* stream);
+/* src bf16 [rows, src_ld] (cols valid) -> dst bf16 [cols, dst_ld]; feeds the gradient GEMM a K-major operand. */
+int mrclip_transpose_bf16(const void* src, int rows, int cols, long src_ld, void* dst, long dst_ld,
+                          void* stream);
+
+/* ---- ClipLoss forward (reference loss.py:104-139, get_logits + 2x F.cross_entropy) -------------- */
+/* Streams the tiles S = scale * A * B[col_begin:col_end]^T through TMEM and leaves online-LSE
+ * partials in `ws`.  May be called several times on disjoint column ranges (e.g. local columns while
+ * the all-gather of the rest is in flight); together the calls must cover [0, n_cols). */
+int mrclip_clip_fwd_tiles(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
+                          const float* scale, int col_begin, int col_end, void* ws, void* stream);
+/* Reduces the partials: lse2_row[m_rows]; per-column (max2,sum) over this rank's rows col_m/col_l[n_cols];
+ * diag2[m_rows] = positive logit in log2 units. */
+int mrclip_clip_fwd_reduce(mrclip_shape shape, void* ws, float* lse2_row, float* col_m, float* col_l,
+                           float* diag2, void* stream);
+/* Merges `parts` (max2,sum) partial vectors (element j of part w at [w*part_stride + j]) into
+ * lse2_out[mrclip_padded_cols(n_cols)] (+inf in the padding). */
+int mrclip_lse2_merge(const float* part_m, const float* part_l, int parts, long part_stride, int n_cols,
+                      float* lse2_out, void* stream);
+/* loss[0] = (CE_image + CE_text)/2 over this rank's rows (natural log), loss.py:134-137. */
+int mrclip_clip_loss(const float* lse2_row, const float* lse2_col, const float* diag2, int m_rows,
+                     int label_offset, float* loss, void* stream);
+
+/* ---- ClipLoss backward row pass (autograd of loss.py:117-137 for one operand) -------------------- */
+/* d_a[m_rows, d] = coef * scale * grad_out * sum_j G_ij * B_j   with
+ *   G_ij = w_own * exp(S_ij - lse_a_i) + w_oth * exp(S_ij - lse_b_j) - (w_own + w_oth) * [j == label_i]
+ * d_scale (+)= coef * grad_out * w_own * (sum_ij exp(S_ij - lse_a_i) * C_ij - sum_i C_ii),  C = A * B^T.
+ * bt_all is B transposed ([ld, bt_ld] bf16).  lse2_b must be the padded vector from mrclip_lse2_merge.
+ * grad_out may be NULL (= 1).  d_scale may be NULL. */
+int mrclip_clip_bwd(const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
+                    mrclip_shape shape, int ld, const float* lse2_a, const float* lse2_b,
+                    const float* scale, float w_own, float w_oth, float coef, const float* grad_out,
+                    void* ws, void* d_a, int out_dtype, long out_ld, float* d_scale,
+                    int accumulate_scalars, void* stream);
+
+/* ---- SigLipLoss (reference loss.py:342-448) ------------------------------------------------------ */
+/* loss[0] = (1/m_rows) * sum_{i local, j all} softplus(-y_ij (scale * A_i.B_j + bias)), y=+1 iff j==label_i */
+int mrclip_siglip_fwd(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
+                      const float* scale, const float* bias, void* ws, float* loss, void* stream);
+/* d_a = coef * scale * grad_out * sum_j G_ij B_j,  G = sigmoid(z) - [j==label_i];
+ * d_scale (+)= coef*grad_out*sum G*C ; d_bias (+)= coef*grad_out*sum G  (either may be NULL). */
+int mrclip_siglip_bwd(const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
+                      mrclip_shape shape, int ld, const float* scale, const float* bias, float coef,
+                      const float* grad_out, void* ws, void* d_a, int out_dtype, long out_ld,
+                      float* d_scale, float* d_bias, int accumulate_scalars, void* stream);
+
+/* number of kernels this library has launched on behalf of the calling process (for bench accounting) */
+long mrclip_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MRCLIP_H_ */

@@ -1,0 +1,444 @@
+// C-ABI implementation: host-side planning (work decomposition, TMA tensor maps, workspace
+// carving) and kernel launches.  See include/mrclip.h for the contract.
+#include "../../include/mrclip.h"
+#include "aux_kernels.cuh"
+#include "tile_kernel.cuh"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+using namespace mrclip;
+
+thread_local std::string g_err;
+std::atomic<long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                     \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess)                                                                 \
+      return fail((int)e_, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                  __LINE__);                                                               \
+  } while (0)
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+int num_sms() {
+  static int cached = 0;
+  if (cached) return cached;
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+  cached = n;
+  return n;
+}
+
+// ------------------------------------------------------------------ TMA tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// bf16 matrix [rows, cols] with row stride ld elements; box = [box_rows, 64 cols], 128B swizzle
+int make_map(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
+    return fail(-3, "TMA operand not 16-byte aligned (base %p, ld %ld)", base, ld);
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)box_rows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                  estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-4, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+
+// ------------------------------------------------------------------ plans
+struct FwdPlan {
+  int num_rb, num_ct, tiles_per_chunk, total_chunks, m_pad, n_pad, bands;
+};
+FwdPlan fwd_plan(int m_rows, int n_cols) {
+  FwdPlan f;
+  f.num_rb = ceil_div(m_rows, kBM);
+  f.num_ct = ceil_div(n_cols, kBN);
+  const long total = (long)f.num_rb * f.num_ct;
+  long tpc = total / (148L * 8);
+  if (tpc < 1) tpc = 1;
+  if (tpc > 32) tpc = 32;
+  f.tiles_per_chunk = (int)tpc;
+  f.total_chunks = ceil_div(f.num_ct, f.tiles_per_chunk);
+  f.m_pad = f.num_rb * kBM;
+  f.n_pad = f.num_ct * kBN;
+  f.bands = f.m_pad / 32;
+  return f;
+}
+
+struct BwdPlan {
+  int num_rb, num_ct, dc, num_dc, d_pad, cs, tiles_per_chunk, m_pad, n_pad, num_items;
+};
+BwdPlan bwd_plan(int m_rows, int n_cols, int ld) {
+  BwdPlan b;
+  b.num_rb = ceil_div(m_rows, kBM);
+  b.num_ct = ceil_div(n_cols, kBN);
+  b.num_dc = ceil_div(ld, 384);
+  const int dcw = ceil_div(ld, b.num_dc);
+  b.dc = dcw <= 256 ? 256 : 384;
+  b.d_pad = b.num_dc * b.dc;
+  b.m_pad = b.num_rb * kBM;
+  b.n_pad = b.num_ct * kBN;
+  const int sms = num_sms();
+  const int base = b.num_rb * b.num_dc;
+  int best_cs = 1;
+  double best_eff = 0.0;
+  for (int cs = 1; cs <= 32 && cs <= b.num_ct; ++cs) {
+    const int tpc = ceil_div(b.num_ct, cs);
+    if (cs > 1 && tpc < 4) break;
+    const int cs_eff = ceil_div(b.num_ct, tpc);
+    const long items = (long)base * cs_eff;
+    const double eff = (double)items / ((double)ceil_div((int)items, sms) * sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_cs = cs_eff;
+    }
+    if (best_eff >= 0.97) break;
+  }
+  b.tiles_per_chunk = ceil_div(b.num_ct, best_cs);
+  b.cs = ceil_div(b.num_ct, b.tiles_per_chunk);
+  b.num_items = base * b.cs;
+  return b;
+}
+
+struct WsLayout {
+  size_t row_part, col_l, col_c, diag2, sc_part, dpart, total;
+};
+WsLayout ws_layout(int m_rows, int n_cols, int d) {
+  const int ld = mrclip_padded_dim(d);
+  const FwdPlan f = fwd_plan(m_rows, n_cols);
+  const BwdPlan b = bwd_plan(m_rows, n_cols, ld);
+  WsLayout w;
+  size_t off = 0;
+  // forward view
+  w.row_part = off;
+  off += align_up((size_t)f.total_chunks * 2 * f.m_pad * sizeof(float2), 256);
+  w.col_l = off;
+  off += align_up((size_t)f.bands * f.n_pad * sizeof(float), 256);
+  w.col_c = off;
+  off += align_up((size_t)f.bands * (f.n_pad / 64) * sizeof(float), 256);
+  w.diag2 = off;
+  off += align_up((size_t)f.m_pad * sizeof(float), 256);
+  const size_t fwd_end = off;
+  // backward view (aliases the forward view; forward partials are dead by then)
+  w.dpart = 0;
+  const size_t bwd_end = align_up((size_t)b.cs * b.m_pad * b.d_pad * sizeof(float), 256);
+  off = fwd_end > bwd_end ? fwd_end : bwd_end;
+  w.sc_part = off;
+  const size_t items_f = (size_t)f.num_rb * f.total_chunks;
+  const size_t items = items_f > (size_t)b.num_items ? items_f : (size_t)b.num_items;
+  off += align_up(items * kEpiWarps * sizeof(float2), 256);
+  w.total = off;
+  return w;
+}
+
+template <int MODE, int LOSS, int DC>
+int launch_tile(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbt, const TileParams& p,
+                cudaStream_t st) {
+  using Cfg = TileCfg<MODE, LOSS, DC>;
+  auto kern = tile_kernel<MODE, LOSS, DC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  if (grid <= 0) return 0;
+  kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mbt, p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int check_shape(const mrclip_shape& s, int ld) {
+  if (s.m_rows <= 0 || s.n_cols <= 0 || s.d <= 0) return fail(-1, "empty shape (m=%d n=%d d=%d)", s.m_rows, s.n_cols, s.d);
+  if (ld < s.d || ld % 8 != 0) return fail(-1, "ld=%d must be a multiple of 8 and >= d=%d", ld, s.d);
+  if (s.label_offset < 0) return fail(-1, "negative label_offset");
+  return 0;
+}
+
+int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
+            const float* scale, const float* bias, int col_begin, int col_end, void* ws, cudaStream_t st) {
+  if (int e = check_shape(sh, ld)) return e;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  const int granule = f.tiles_per_chunk * kBN;
+  if (col_begin < 0 || col_end > sh.n_cols || col_begin >= col_end) return fail(-1, "bad column range [%d,%d)", col_begin, col_end);
+  if (col_begin % granule != 0) return fail(-1, "col_begin=%d not a multiple of the granule %d", col_begin, granule);
+  if (col_end != sh.n_cols && col_end % granule != 0) return fail(-1, "col_end=%d not a multiple of the granule %d", col_end, granule);
+  CUtensorMap ma, mb;
+  if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kBN)) return e;
+  TileParams p;
+  memset(&p, 0, sizeof p);
+  p.m_rows = sh.m_rows;
+  p.n_cols = sh.n_cols;
+  p.num_kb = ceil_div(ld, kBK);
+  p.num_rb = f.num_rb;
+  p.tile_begin = col_begin / kBN;
+  p.tile_end = ceil_div(col_end, kBN);
+  p.tiles_per_chunk = f.tiles_per_chunk;
+  p.num_chunks = ceil_div(p.tile_end - p.tile_begin, f.tiles_per_chunk);
+  p.chunk_base = p.tile_begin / f.tiles_per_chunk;
+  p.num_dc = 1;
+  p.num_items = p.num_chunks * f.num_rb;
+  p.label_offset = sh.label_offset;
+  p.m_pad = f.m_pad;
+  p.n_pad = f.n_pad;
+  p.d_pad = 0;
+  p.scale = scale;
+  p.bias = bias;
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  p.row_part = reinterpret_cast<float2*>(wsb + w.row_part);
+  p.col_l = reinterpret_cast<float*>(wsb + w.col_l);
+  p.col_c = reinterpret_cast<float*>(wsb + w.col_c);
+  p.diag2 = reinterpret_cast<float*>(wsb + w.diag2);
+  p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
+  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWD, LOSS_CLIP, 256>(ma, mb, mb, p, st);
+  return launch_tile<MODE_FWD, LOSS_SIGLIP, 256>(ma, mb, mb, p, st);
+}
+
+int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
+            const mrclip_shape& sh, int ld, const float* lse2_a, const float* lse2_b, const float* scale,
+            const float* bias, float w_own, float w_oth, float coef, const float* grad_out, void* ws,
+            void* d_a, int out_dtype, long out_ld, float* d_scale, float* d_bias, int accumulate,
+            cudaStream_t st) {
+  if (int e = check_shape(sh, ld)) return e;
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  const BwdPlan b = bwd_plan(sh.m_rows, sh.n_cols, ld);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  if (bt_ld < sh.n_cols || bt_ld % 8 != 0) return fail(-1, "bt_ld=%ld must be a multiple of 8 and >= n_cols", bt_ld);
+  CUtensorMap ma, mb, mbt;
+  if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kBN)) return e;
+  if (int e = make_map(&mbt, bt_all, ld, sh.n_cols, bt_ld, b.dc == 384 ? 192 : 256)) return e;
+  TileParams p;
+  memset(&p, 0, sizeof p);
+  p.m_rows = sh.m_rows;
+  p.n_cols = sh.n_cols;
+  p.num_kb = ceil_div(ld, kBK);
+  p.num_rb = b.num_rb;
+  p.tile_begin = 0;
+  p.tile_end = b.num_ct;
+  p.tiles_per_chunk = b.tiles_per_chunk;
+  p.num_chunks = b.cs;
+  p.chunk_base = 0;
+  p.num_dc = b.num_dc;
+  p.num_items = b.num_items;
+  p.label_offset = sh.label_offset;
+  p.m_pad = b.m_pad;
+  p.n_pad = b.n_pad;
+  p.d_pad = b.d_pad;
+  p.scale = scale;
+  p.bias = bias;
+  p.w_own = w_own;
+  p.w_oth = w_oth;
+  p.lse2_a = lse2_a;
+  p.lse2_b = lse2_b;
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  p.dpart = reinterpret_cast<float*>(wsb + w.dpart);
+  p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part);
+  int e = 0;
+  if (loss_kind == LOSS_CLIP)
+    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_CLIP, 384>(ma, mb, mbt, p, st)
+                    : launch_tile<MODE_BWD, LOSS_CLIP, 256>(ma, mb, mbt, p, st);
+  else
+    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_SIGLIP, 384>(ma, mb, mbt, p, st)
+                    : launch_tile<MODE_BWD, LOSS_SIGLIP, 256>(ma, mb, mbt, p, st);
+  if (e) return e;
+  {
+    const long total = (long)sh.m_rows * (b.d_pad / 4);
+    const int threads = 256;
+    long blocks = (total + threads - 1) / threads;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    grad_reduce_kernel<<<(int)blocks, threads, 0, st>>>(p.dpart, b.cs, sh.m_rows, sh.d, b.m_pad, b.d_pad, coef,
+                                                        scale, grad_out, d_a, out_dtype, out_ld);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+  }
+  if (d_scale || d_bias) {
+    const float cx = coef * (loss_kind == LOSS_CLIP ? w_own : 1.f);
+    scalar_reduce_kernel<<<1, 1024, 0, st>>>(p.sc_part, (long)b.num_items * kEpiWarps, cx, coef, grad_out,
+                                             nullptr, d_scale, d_bias, accumulate);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mrclip_version(void) { return 100; }
+const char* mrclip_last_error(void) { return g_err.c_str(); }
+long mrclip_launch_count(void) { return g_launches.load(); }
+
+int mrclip_device_ok(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    return 0;
+  }
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10 ? 1 : 0;
+}
+
+int mrclip_padded_dim(int d) { return (d + 7) / 8 * 8; }
+int mrclip_padded_cols(int n_cols) { return (n_cols + kBN - 1) / kBN * kBN; }
+
+size_t mrclip_workspace_bytes(int m_rows, int n_cols, int d) {
+  if (m_rows <= 0 || n_cols <= 0 || d <= 0) return 0;
+  return ws_layout(m_rows, n_cols, d).total;
+}
+
+int mrclip_fwd_col_granule(int m_rows, int n_cols) {
+  if (m_rows <= 0 || n_cols <= 0) return kBN;
+  return fwd_plan(m_rows, n_cols).tiles_per_chunk * kBN;
+}
+
+int mrclip_pack_bf16(const void* src, int src_dtype, int rows, int d, long src_ld, void* dst, int dst_ld,
+                     void* stream) {
+  if (rows <= 0 || d <= 0) return fail(-1, "empty pack");
+  if (src_dtype < 0 || src_dtype > 2) return fail(-1, "bad dtype %d", src_dtype);
+  if (dst_ld < d) return fail(-1, "dst_ld < d");
+  const long total = (long)rows * dst_ld;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, rows, d, src_ld,
+                                                                  (__nv_bfloat16*)dst, dst_ld);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_transpose_bf16(const void* src, int rows, int cols, long src_ld, void* dst, long dst_ld,
+                          void* stream) {
+  if (rows <= 0 || cols <= 0) return fail(-1, "empty transpose");
+  dim3 grid((cols + 63) / 64, (rows + 63) / 64), block(32, 8);
+  transpose_bf16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, rows, cols,
+                                                                  src_ld, (__nv_bfloat16*)dst, dst_ld);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_clip_fwd_tiles(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
+                          const float* scale, int col_begin, int col_end, void* ws, void* stream) {
+  return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws,
+                 (cudaStream_t)stream);
+}
+
+int mrclip_clip_fwd_reduce(mrclip_shape sh, void* ws, float* lse2_row, float* col_m, float* col_l,
+                           float* diag2, void* stream) {
+  if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  reduce_rows_kernel<<<ceil_div(sh.m_rows, 256), 256, 0, st>>>(
+      reinterpret_cast<const float2*>(wsb + w.row_part), f.total_chunks * 2, sh.m_rows, f.m_pad, lse2_row);
+  reduce_cols_kernel<<<ceil_div(sh.n_cols, 256), 256, 0, st>>>(
+      reinterpret_cast<const float*>(wsb + w.col_l), reinterpret_cast<const float*>(wsb + w.col_c),
+      ceil_div(sh.m_rows, 32), sh.n_cols, f.n_pad, col_m, col_l);
+  g_launches.fetch_add(2);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(diag2, wsb + w.diag2, (size_t)sh.m_rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+int mrclip_lse2_merge(const float* part_m, const float* part_l, int parts, long part_stride, int n_cols,
+                      float* lse2_out, void* stream) {
+  if (parts <= 0 || n_cols <= 0) return fail(-1, "empty merge");
+  const int n_pad = mrclip_padded_cols(n_cols);
+  merge_parts_kernel<<<ceil_div(n_pad, 256), 256, 0, (cudaStream_t)stream>>>(part_m, part_l, parts, n_cols,
+                                                                            part_stride, n_pad, lse2_out);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_clip_loss(const float* lse2_row, const float* lse2_col, const float* diag2, int m_rows,
+                     int label_offset, float* loss, void* stream) {
+  if (m_rows <= 0) return fail(-1, "empty loss");
+  clip_loss_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(lse2_row, lse2_col, diag2, m_rows, label_offset,
+                                                         loss);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_clip_bwd(const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
+                    mrclip_shape shape, int ld, const float* lse2_a, const float* lse2_b,
+                    const float* scale, float w_own, float w_oth, float coef, const float* grad_out,
+                    void* ws, void* d_a, int out_dtype, long out_ld, float* d_scale,
+                    int accumulate_scalars, void* stream) {
+  return run_bwd(LOSS_CLIP, a_rows, b_all, bt_all, bt_ld, shape, ld, lse2_a, lse2_b, scale, nullptr, w_own,
+                 w_oth, coef, grad_out, ws, d_a, out_dtype, out_ld, d_scale, nullptr, accumulate_scalars,
+                 (cudaStream_t)stream);
+}
+
+int mrclip_siglip_fwd(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
+                      const float* scale, const float* bias, void* ws, float* loss, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = run_fwd(LOSS_SIGLIP, a_rows, b_all, shape, ld, scale, bias, 0, shape.n_cols, ws, st)) return e;
+  const FwdPlan f = fwd_plan(shape.m_rows, shape.n_cols);
+  const WsLayout w = ws_layout(shape.m_rows, shape.n_cols, shape.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
+                                           (long)f.num_rb * f.total_chunks * kEpiWarps,
+                                           1.f / (float)shape.m_rows, 0.f, nullptr, nullptr, loss, nullptr, 0);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_siglip_bwd(const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
+                      mrclip_shape shape, int ld, const float* scale, const float* bias, float coef,
+                      const float* grad_out, void* ws, void* d_a, int out_dtype, long out_ld,
+                      float* d_scale, float* d_bias, int accumulate_scalars, void* stream) {
+  return run_bwd(LOSS_SIGLIP, a_rows, b_all, bt_all, bt_ld, shape, ld, nullptr, nullptr, scale, bias, 1.f, 0.f,
+                 coef, grad_out, ws, d_a, out_dtype, out_ld, d_scale, d_bias, accumulate_scalars,
+                 (cudaStream_t)stream);
+}
+
+}  // extern "C"

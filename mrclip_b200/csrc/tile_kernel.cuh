@@ -1,0 +1,540 @@
+// The tile kernel: a persistent, warp-specialised tcgen05 GEMM whose accumulators never leave
+// the SM.  One CTA per SM walks a list of work items; inside an item it streams 128x128 tiles
+// of  S = A * B^T  (A = this rank's 128-row block, B = a 128-row block of the other modality)
+// through TMEM and consumes them in registers:
+//
+//   MODE_FWD : per-row / per-column online log-sum-exp partials (ClipLoss) or the summed
+//              softplus (SigLipLoss).  Nothing N x N is written anywhere.
+//   MODE_BWD : recomputes S, turns it into the gradient tile G (bf16, written to shared memory
+//              in the UMMA K-major swizzled layout) and immediately contracts it with B again:
+//              dA[128, DC] += G[128,128] * B[128 cols, DC]   (second tcgen05 GEMM, accumulator
+//              stationary in TMEM for the whole item).
+//
+// Replaces, for the reference (src/open_clip/loss.py): the logits GEMMs :117-124, the two
+// F.cross_entropy calls :135-136 and their autograd graph; SigLipLoss._loss :354-363.
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
+// issuer, warps 2..9 = epilogue (two warps per TMEM lane quarter, each taking 64 of the 128
+// tile columns).
+#pragma once
+#include "ptx.cuh"
+#include <cuda_bf16.h>
+#include <math_constants.h>
+
+namespace mrclip {
+
+constexpr int kBM = 128;           // tile rows  (= TMEM lanes)
+constexpr int kBN = 128;           // tile cols of S
+constexpr int kBK = 64;            // K block: 64 bf16 = one 128-byte swizzle row
+constexpr int kStageBytes = 32768; // one pipeline slot: A(16K)+B(16K) or one Bt block (<=32K)
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 64 + 32 * kEpiWarps;
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+enum : int { MODE_FWD = 0, MODE_BWD = 1 };
+enum : int { LOSS_CLIP = 0, LOSS_SIGLIP = 1 };
+
+struct TileParams {
+  int m_rows;           // rows of A owned by this launch
+  int n_cols;           // rows of B (= columns of S)
+  int num_kb;           // ceil(d / 64)
+  int num_rb;           // ceil(m_rows / 128)
+  int tile_begin;       // first column tile handled by this launch
+  int tile_end;         // one past the last column tile
+  int tiles_per_chunk;  // column tiles per work item
+  int num_chunks;       // chunks in [tile_begin, tile_end)
+  int chunk_base;       // global index of the first chunk (FWD partial slots)
+  int num_dc;           // BWD: number of D chunks
+  int num_items;
+  int label_offset;     // global column of row 0's positive
+  int m_pad, n_pad, d_pad;
+  const float* scale;   // device scalar: exp'd logit_scale
+  const float* bias;    // device scalar or null (SigLIP)
+  float w_own, w_oth;   // weights of the own-direction / other-direction softmax terms
+  // FWD (clip)
+  float2* row_part;     // [slots][m_pad]   (max2, sum)
+  float* col_l;         // [bands][n_pad]
+  float* col_c;         // [bands][n_pad/64]
+  float* diag2;         // [m_pad]  positive logit in log2 units
+  // FWD (siglip) / BWD scalar partials
+  float2* sc_part;      // [num_items * 8]
+  // BWD
+  const float* lse2_a;  // [m_rows]   own-direction LSE of each A row (log2 units)
+  const float* lse2_b;  // [n_pad]    other-direction LSE of each B row, +inf padded
+  float* dpart;         // [cs][m_pad][d_pad]
+};
+
+template <int LEN, int OFF>
+__device__ __forceinline__ void butterfly_step(float (&v)[64], uint32_t lane) {
+  const bool upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < LEN / 2; ++i) {
+    const float keep = upper ? v[i + LEN / 2] : v[i];
+    const float send = upper ? v[i] : v[i + LEN / 2];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+}
+
+__device__ __forceinline__ float log1p_from_exp(float e) {
+  // log(1+e) for e in [0,1]; series below 1/8 (lg2.approx is not accurate enough near 1)
+  const float series = e * (1.f + e * (-0.5f + e * (0.33333334f + e * (-0.25f + e * 0.2f))));
+  const float direct = lg2f(1.f + e) * kLn2;
+  return e <= 0.125f ? series : direct;
+}
+
+template <int MODE, int LOSS, int DC>
+struct TileCfg {
+  static constexpr int kSBufs = (MODE == MODE_FWD) ? 2 : (DC == 256 ? 2 : 1);
+  static constexpr int kTmemCols = (MODE == MODE_FWD) ? 256 : 512;
+  static constexpr int kDaCol = kSBufs * kBN;
+  static constexpr int kNSub = (DC == 384) ? 2 : 1;
+  static constexpr int kDN = DC / kNSub;
+  static constexpr int kStages = (MODE == MODE_FWD) ? 6 : 5;
+  static constexpr int kGBytes = (MODE == MODE_BWD) ? 2 * 32768 : 0;
+  static constexpr int kNumBars = 2 * kStages + 10;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kNumBars * 8 + 16 + 1024;
+};
+
+template <int MODE, int LOSS, int DC>
+__global__ void __launch_bounds__(kThreads, 1)
+tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmBt, const TileParams p) {
+  using Cfg = TileCfg<MODE, LOSS, DC>;
+  constexpr int STAGES = Cfg::kStages;
+  constexpr int NSB = Cfg::kSBufs;
+  constexpr int DN = Cfg::kDN;
+  constexpr int NSUB = Cfg::kNSub;
+  constexpr uint32_t IDESC_S = make_idesc_bf16(kBM, kBN);
+  constexpr uint32_t IDESC_D = make_idesc_bf16(kBM, DN);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_base = smem_u32(smem);
+  const uint32_t g_base = stage_base + STAGES * kStageBytes;
+  uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes;
+  const uint32_t bar_base = smem_u32(bar_ptr);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + Cfg::kNumBars * 8);
+
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto bar_sfull = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto bar_sempty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+  auto bar_gfull = [&](int b) { return bar_base + 8u * (2 * STAGES + 4 + b); };
+  auto bar_gempty = [&](int b) { return bar_base + 8u * (2 * STAGES + 6 + b); };
+  const uint32_t bar_dafull = bar_base + 8u * (2 * STAGES + 8);
+  const uint32_t bar_daempty = bar_base + 8u * (2 * STAGES + 9);
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (MODE == MODE_BWD) tma_prefetch_desc(&tmBt);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_full(s), 1);
+        mbar_init(bar_empty(s), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_sfull(b), 1);
+        mbar_init(bar_sempty(b), kEpiWarps);
+        mbar_init(bar_gfull(b), kEpiWarps);
+        mbar_init(bar_gempty(b), 1);
+      }
+      mbar_init(bar_dafull, 1);
+      mbar_init(bar_daempty, kEpiWarps);
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), Cfg::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item -> (row block, D chunk, column-tile range)
+  auto decode = [&](int item, int& rb, int& dc, int& chunk, int& t0, int& t1) {
+    rb = item % p.num_rb;
+    int rest = item / p.num_rb;
+    if (MODE == MODE_BWD) {
+      dc = rest % p.num_dc;
+      rest /= p.num_dc;
+    } else {
+      dc = 0;
+    }
+    chunk = rest;
+    t0 = p.tile_begin + chunk * p.tiles_per_chunk;
+    t1 = min(t0 + p.tiles_per_chunk, p.tile_end);
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int rb, dc, chunk, t0, t1;
+        decode(item, rb, dc, chunk, t0, t1);
+        auto load_s = [&](int t) {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(bar_empty(stage), phase ^ 1);
+            mbar_expect_tx(bar_full(stage), 2 * kBM * kBK * 2);
+            const uint32_t dst = stage_base + stage * kStageBytes;
+            tma_load_2d(dst, &tmA, bar_full(stage), kb * kBK, rb * kBM);
+            tma_load_2d(dst + kBM * kBK * 2, &tmB, bar_full(stage), kb * kBK, t * kBN);
+            advance();
+          }
+        };
+        auto load_d = [&](int t) {
+          for (int kb2 = 0; kb2 < kBN / kBK; ++kb2) {
+            for (int sub = 0; sub < NSUB; ++sub) {
+              mbar_wait(bar_empty(stage), phase ^ 1);
+              mbar_expect_tx(bar_full(stage), DN * kBK * 2);
+              tma_load_2d(stage_base + stage * kStageBytes, &tmBt, bar_full(stage),
+                          t * kBN + kb2 * kBK, dc * DC + sub * DN);
+              advance();
+            }
+          }
+        };
+        if (MODE == MODE_FWD) {
+          for (int t = t0; t < t1; ++t) load_s(t);
+        } else {
+          load_s(t0);
+          for (int t = t0; t < t1; ++t) {
+            if (t + 1 < t1) load_s(t + 1);
+            load_d(t);
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      auto advance = [&]() {
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      uint32_t s_use = 0, g_use = 0, item_count = 0;
+      for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+        int rb, dc, chunk, t0, t1;
+        decode(item, rb, dc, chunk, t0, t1);
+        auto mma_s = [&]() {
+          const uint32_t buf = s_use % NSB, use = s_use / NSB;
+          mbar_wait(bar_sempty(buf), (use & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + buf * kBN;
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(bar_full(stage), phase);
+            tc_fence_after();
+            const uint32_t a = stage_base + stage * kStageBytes;
+            const uint32_t b = a + kBM * kBK * 2;
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k) {
+              umma_bf16(d_tmem, make_kmajor_sw128_desc(a + k * 32), make_kmajor_sw128_desc(b + k * 32),
+                        IDESC_S, (kb | k) != 0 ? 1u : 0u);
+            }
+            umma_commit(bar_empty(stage));
+            advance();
+          }
+          umma_commit(bar_sfull(buf));
+          ++s_use;
+        };
+        auto mma_d = [&](bool first) {
+          const uint32_t gb = g_use & 1, use = g_use >> 1;
+          mbar_wait(bar_gfull(gb), use & 1);
+          tc_fence_after();
+          if (first) {
+            mbar_wait(bar_daempty, (item_count & 1) ^ 1);
+            tc_fence_after();
+          }
+          for (int kb2 = 0; kb2 < kBN / kBK; ++kb2) {
+            for (int sub = 0; sub < NSUB; ++sub) {
+              mbar_wait(bar_full(stage), phase);
+              tc_fence_after();
+              const uint32_t a = g_base + gb * 32768 + kb2 * 16384;
+              const uint32_t b = stage_base + stage * kStageBytes;
+#pragma unroll
+              for (int k = 0; k < kBK / 16; ++k) {
+                umma_bf16(tmem_base + Cfg::kDaCol + sub * DN, make_kmajor_sw128_desc(a + k * 32),
+                          make_kmajor_sw128_desc(b + k * 32), IDESC_D,
+                          (first && kb2 == 0 && k == 0) ? 0u : 1u);
+              }
+              umma_commit(bar_empty(stage));
+              advance();
+            }
+          }
+          umma_commit(bar_gempty(gb));
+          ++g_use;
+        };
+        if (MODE == MODE_FWD) {
+          for (int t = t0; t < t1; ++t) mma_s();
+        } else {
+          mma_s();
+          for (int t = t0; t < t1; ++t) {
+            if (t + 1 < t1) mma_s();
+            mma_d(t == t0);
+          }
+          umma_commit(bar_dafull);
+          ++item_count;
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue warps
+    const uint32_t q = warp & 3;          // TMEM lane quarter this warp may touch
+    const uint32_t h = (warp - 2) >> 2;   // which 64-column half of the tile
+    const uint32_t row_in_tile = q * 32 + lane;
+    const float s = __ldg(p.scale);
+    const float sl = s * kLog2e;
+    float bias = 0.f;
+    if (LOSS == LOSS_SIGLIP && p.bias != nullptr) bias = __ldg(p.bias);
+    const float b2 = bias * kLog2e;
+    uint32_t s_use = 0, g_use = 0, item_count = 0;
+
+    for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
+      int rb, dc, chunk, t0, t1;
+      decode(item, rb, dc, chunk, t0, t1);
+      const int grow = rb * kBM + row_in_tile;
+      const bool row_valid = grow < p.m_rows;
+      const int label = grow + p.label_offset;
+      const int label_w0 = rb * kBM + q * 32 + p.label_offset;  // label of lane 0 (warp uniform)
+
+      float m_run = -CUDART_INF_F, l_run = 0.f;  // FWD clip: running row (max2, sum)
+      float acc0 = 0.f, acc1 = 0.f;              // scalar partials (loss | ds, db)
+      float lr2 = CUDART_INF_F;
+      if (MODE == MODE_BWD && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
+
+      for (int t = t0; t < t1; ++t) {
+        const uint32_t buf = s_use % NSB, use = s_use / NSB;
+        mbar_wait(bar_sfull(buf), use & 1);
+        tc_fence_after();
+        uint32_t raw[64];
+        {
+          const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * kBN + h * 64;
+          uint32_t r0[32], r1[32];
+          tmem_ld_32x32(taddr, r0);
+          tmem_ld_32x32(taddr + 32, r1);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            raw[c] = r0[c];
+            raw[c + 32] = r1[c];
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_sempty(buf));
+        ++s_use;
+
+        const int col_base = t * kBN + h * 64;
+        const bool ragged = (col_base + 64 > p.n_cols);  // warp uniform
+        const bool diag_here = (label_w0 + 31 >= col_base) && (label_w0 < col_base + 64);
+
+        if (MODE == MODE_FWD && LOSS == LOSS_CLIP) {
+          float v[64];
+#pragma unroll
+          for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(raw[c]) * sl;
+          if (diag_here && row_valid) {
+            const int idx = label - col_base;
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c == idx) p.diag2[grow] = v[c];
+          }
+          if (ragged) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (col_base + c >= p.n_cols) v[c] = -CUDART_INF_F;
+          }
+          if (!row_valid) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) v[c] = -CUDART_INF_F;
+          }
+          float tmax = v[0];
+#pragma unroll
+          for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, v[c]);
+          float cw = warp_max(tmax);
+          if (cw == -CUDART_INF_F) cw = 0.f;
+          float rowsum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            v[c] = ex2f(v[c] - cw);
+            rowsum += v[c];
+          }
+          const float mnew = fmaxf(m_run, cw);
+          l_run = l_run * ex2f(m_run - mnew) + rowsum * ex2f(cw - mnew);
+          m_run = mnew;
+          butterfly_step<64, 16>(v, lane);
+          butterfly_step<32, 8>(v, lane);
+          butterfly_step<16, 4>(v, lane);
+          butterfly_step<8, 2>(v, lane);
+          butterfly_step<4, 1>(v, lane);
+          const int band = rb * 4 + q;
+          *reinterpret_cast<float2*>(p.col_l + (size_t)band * p.n_pad + col_base + 2 * lane) =
+              make_float2(v[0], v[1]);
+          if (lane == 0) p.col_c[(size_t)band * (p.n_pad / 64) + col_base / 64] = cw;
+        } else if (MODE == MODE_FWD && LOSS == LOSS_SIGLIP) {
+          float part = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; ++c) {
+            const float a = __uint_as_float(raw[c]);
+            const float z = fmaf(a, s, bias);
+            const float u = fmaf(a, sl, b2);
+            float sp = fmaxf(z, 0.f) + log1p_from_exp(ex2f(-fabsf(u)));
+            if (ragged && (col_base + c >= p.n_cols)) sp = 0.f;
+            part += sp;
+          }
+          if (diag_here) {
+            const int idx = label - col_base;
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c == idx) part -= fmaf(__uint_as_float(raw[c]), s, bias);
+          }
+          if (row_valid) acc0 += part;
+        } else {
+          // ------------------------------------------------------------- BWD: build G
+          const uint32_t gb = g_use & 1, guse = g_use >> 1;
+          mbar_wait(bar_gempty(gb), (guse & 1) ^ 1);
+          const uint32_t grow_smem =
+              g_base + gb * 32768 + h * 16384 + row_in_tile * 128;
+          float dsum = 0.f, bsum = 0.f;
+#pragma unroll
+          for (int ck = 0; ck < 8; ++ck) {
+            float g[8];
+            if (LOSS == LOSS_CLIP) {
+              const float4 lb0 =
+                  __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8));
+              const float4 lb1 =
+                  __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8 + 4));
+              const float lb[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = __uint_as_float(raw[ck * 8 + j]);
+                const float tt = a * sl;
+                const float p_own = ex2f(tt - lr2);
+                const float p_oth = ex2f(tt - lb[j]);
+                g[j] = p.w_own * p_own + p.w_oth * p_oth;
+                dsum = fmaf(p_own, a, dsum);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float a = __uint_as_float(raw[ck * 8 + j]);
+                const float u = fmaf(a, sl, b2);
+                float gg = rcpf(1.f + ex2f(-u));
+                if (!row_valid) gg = 0.f;
+                g[j] = gg;
+              }
+            }
+            if (ragged) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                if (col_base + ck * 8 + j >= p.n_cols) g[j] = 0.f;
+            }
+            if (LOSS == LOSS_SIGLIP) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                dsum = fmaf(g[j], __uint_as_float(raw[ck * 8 + j]), dsum);
+                bsum += g[j];
+              }
+            }
+            if (diag_here) {
+              const int idx = label - col_base - ck * 8;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (j == idx && row_valid) {
+                  const float a = __uint_as_float(raw[ck * 8 + j]);
+                  if (LOSS == LOSS_CLIP) {
+                    g[j] -= (p.w_own + p.w_oth);
+                    dsum -= a;
+                  } else {
+                    g[j] -= 1.f;
+                    dsum -= a;
+                    bsum -= 1.f;
+                  }
+                }
+              }
+            }
+            const uint32_t dst = grow_smem + ((static_cast<uint32_t>(ck) ^ (row_in_tile & 7)) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                         "r"(pack_bf16x2(g[0], g[1])), "r"(pack_bf16x2(g[2], g[3])),
+                         "r"(pack_bf16x2(g[4], g[5])), "r"(pack_bf16x2(g[6], g[7]))
+                         : "memory");
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_gfull(gb));
+          ++g_use;
+          acc0 += dsum;
+          acc1 += bsum;
+        }
+      }  // tiles
+
+      // ------------------------------------------------------------------ item outputs
+      if (MODE == MODE_FWD && LOSS == LOSS_CLIP) {
+        const int slot = (p.chunk_base + chunk) * 2 + h;
+        p.row_part[(size_t)slot * p.m_pad + grow] = make_float2(m_run, l_run);
+      } else if (MODE == MODE_FWD) {
+        const float tot = warp_sum(acc0);
+        if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(tot, 0.f);
+      } else {
+        mbar_wait(bar_dafull, item_count & 1);
+        tc_fence_after();
+        float* out_row = p.dpart + ((size_t)chunk * p.m_pad + grow) * p.d_pad + dc * DC;
+#pragma unroll 1
+        for (int c0 = h * (DC / 2); c0 < (int)(h + 1) * (DC / 2); c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + Cfg::kDaCol + c0, r);
+          tmem_ld_wait();
+          if (row_valid) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o;
+              o.x = __uint_as_float(r[4 * j + 0]);
+              o.y = __uint_as_float(r[4 * j + 1]);
+              o.z = __uint_as_float(r[4 * j + 2]);
+              o.w = __uint_as_float(r[4 * j + 3]);
+              *reinterpret_cast<float4*>(out_row + c0 + 4 * j) = o;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_daempty);
+        ++item_count;
+        if (dc != 0) {
+          acc0 = 0.f;
+          acc1 = 0.f;
+        }
+        const float t0s = warp_sum(acc0);
+        const float t1s = warp_sum(acc1);
+        if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(t0s, t1s);
+      }
+    }  // items
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace mrclip
