@@ -7,6 +7,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -95,6 +96,7 @@ FwdPlan fwd_plan(int m_rows, int n_cols) {
   long tpc = total / (148L * 8);
   if (tpc < 1) tpc = 1;
   if (tpc > 32) tpc = 32;
+  while (tpc & (tpc - 1)) tpc &= tpc - 1;  // power of two, so per-rank column ranges stay chunk aligned
   f.tiles_per_chunk = (int)tpc;
   f.total_chunks = ceil_div(f.num_ct, f.tiles_per_chunk);
   f.m_pad = f.num_rb * kBM;
@@ -179,7 +181,11 @@ int launch_tile(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap&
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_set = true;
   }
-  const int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  if (const char* g = getenv("MRCLIP_GRID")) {  // experiment knob: cap the number of persistent CTAs
+    const int cap = atoi(g);
+    if (cap > 0 && cap < grid) grid = cap;
+  }
   if (grid <= 0) return 0;
   kern<<<grid, kThreads, Cfg::kSmemBytes, st>>>(ma, mb, mbt, p);
   g_launches.fetch_add(1);

@@ -1,0 +1,114 @@
+"""Kernel engine: the handful of device operations the loss modules are built from.
+
+``CudaEngine`` forwards every call to the C ABI (``libmrclip.so``) on the current torch CUDA stream;
+torch is used only to own device memory.  The interface is deliberately small so that the
+multi-rank orchestration in ``loss.py`` can be exercised on CPU by tests with a stand-in engine
+(tests provide it; the product never constructs anything but ``CudaEngine``).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _cabi
+
+_DT = {torch.float32: _cabi.DT_F32, torch.bfloat16: _cabi.DT_BF16, torch.float16: _cabi.DT_F16}
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+class CudaEngine:
+    """Runs the hot path through the hand-written sm_100a kernels.  No fallback."""
+
+    name = "cuda-sm100a"
+
+    def __init__(self):
+        self.lib = _cabi.load()
+        if not torch.cuda.is_available():
+            raise RuntimeError("mrclip_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        if not self.lib.mrclip_device_ok():
+            raise RuntimeError("mrclip_b200 kernels are built for sm_100a (B200) only")
+
+    # ---- geometry helpers -------------------------------------------------------------------
+    def padded_dim(self, d):
+        return self.lib.mrclip_padded_dim(d)
+
+    def padded_cols(self, n):
+        return self.lib.mrclip_padded_cols(n)
+
+    def workspace_bytes(self, m, n, d):
+        return self.lib.mrclip_workspace_bytes(m, n, d)
+
+    def fwd_col_granule(self, m, n):
+        return self.lib.mrclip_fwd_col_granule(m, n)
+
+    def launch_count(self):
+        return self.lib.mrclip_launch_count()
+
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    # ---- data movement ----------------------------------------------------------------------
+    def pack(self, src, dst):
+        """src [rows, d] (fp32/bf16/fp16, row stride arbitrary) -> dst bf16 [rows, ld] zero padded."""
+        assert src.dim() == 2 and src.stride(1) == 1 and dst.dtype == torch.bfloat16 and dst.is_contiguous()
+        _cabi.check(self.lib.mrclip_pack_bf16(src.data_ptr(), _DT[src.dtype], src.shape[0], src.shape[1],
+                                              src.stride(0), dst.data_ptr(), dst.shape[1], self._stream()))
+
+    def transpose(self, src, dst):
+        """src bf16 [rows, ld] -> dst bf16 [ld, npad]."""
+        _cabi.check(self.lib.mrclip_transpose_bf16(src.data_ptr(), src.shape[0], src.shape[1], src.stride(0),
+                                                   dst.data_ptr(), dst.stride(0), self._stream()))
+
+    # ---- ClipLoss ---------------------------------------------------------------------------
+    def clip_fwd_tiles(self, a_rows, b_all, shape, scale, col_begin, col_end, ws):
+        _cabi.check(self.lib.mrclip_clip_fwd_tiles(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                   scale.data_ptr(), col_begin, col_end, ws.data_ptr(),
+                                                   self._stream()))
+
+    def clip_fwd_reduce(self, shape, ws, lse2_row, col_m, col_l, diag2):
+        _cabi.check(self.lib.mrclip_clip_fwd_reduce(shape, ws.data_ptr(), lse2_row.data_ptr(), col_m.data_ptr(),
+                                                    col_l.data_ptr(), diag2.data_ptr(), self._stream()))
+
+    def lse2_merge(self, part_m, part_l, parts, stride, n_cols, out):
+        _cabi.check(self.lib.mrclip_lse2_merge(part_m.data_ptr(), part_l.data_ptr(), parts, stride, n_cols,
+                                               out.data_ptr(), self._stream()))
+
+    def clip_loss(self, lse2_row, lse2_col, diag2, m_rows, label_offset, loss):
+        _cabi.check(self.lib.mrclip_clip_loss(lse2_row.data_ptr(), lse2_col.data_ptr(), diag2.data_ptr(), m_rows,
+                                              label_offset, loss.data_ptr(), self._stream()))
+
+    def clip_bwd(self, a_rows, b_all, bt_all, shape, lse2_a, lse2_b, scale, w_own, w_oth, coef, grad_out, ws,
+                 d_a, d_scale, accumulate):
+        _cabi.check(self.lib.mrclip_clip_bwd(a_rows.data_ptr(), b_all.data_ptr(), bt_all.data_ptr(),
+                                             bt_all.stride(0), shape, b_all.shape[1], lse2_a.data_ptr(),
+                                             lse2_b.data_ptr(), scale.data_ptr(), w_own, w_oth, coef,
+                                             _ptr(grad_out), ws.data_ptr(), d_a.data_ptr(), _DT[d_a.dtype],
+                                             d_a.stride(0), _ptr(d_scale), int(accumulate), self._stream()))
+
+    # ---- SigLipLoss -------------------------------------------------------------------------
+    def siglip_fwd(self, a_rows, b_all, shape, scale, bias, ws, loss):
+        _cabi.check(self.lib.mrclip_siglip_fwd(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                               scale.data_ptr(), _ptr(bias), ws.data_ptr(), loss.data_ptr(),
+                                               self._stream()))
+
+    def siglip_bwd(self, a_rows, b_all, bt_all, shape, scale, bias, coef, grad_out, ws, d_a, d_scale, d_bias,
+                   accumulate):
+        _cabi.check(self.lib.mrclip_siglip_bwd(a_rows.data_ptr(), b_all.data_ptr(), bt_all.data_ptr(),
+                                               bt_all.stride(0), shape, b_all.shape[1], scale.data_ptr(),
+                                               _ptr(bias), coef, _ptr(grad_out), ws.data_ptr(), d_a.data_ptr(),
+                                               _DT[d_a.dtype], d_a.stride(0), _ptr(d_scale), _ptr(d_bias),
+                                               int(accumulate), self._stream()))
+
+
+_default_engine = None
+
+
+def default_engine():
+    """The process-wide CudaEngine (created on first use; raises when the GPU path is unavailable)."""
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = CudaEngine()
+    return _default_engine

@@ -1,0 +1,439 @@
+"""Drop-in ``ClipLoss`` / ``SigLipLoss`` / ``gather_features`` for MR-CLIP on B200.
+
+Same constructor and call signatures as the reference (``src/open_clip/loss.py``:
+``gather_features`` :21-65, ``ClipLoss`` :68-139, ``SigLipLoss`` :314-448), so
+``open_clip.factory.create_loss`` (factory.py:432-503) and ``train_one_epoch`` (train.py:128)
+use it unchanged.  Behind the signatures the N x N logit matrix never exists: the forward runs the
+tcgen05 tile kernel with a fused online log-sum-exp, the backward re-runs the tiles and contracts
+the gradient tile in TMEM (``csrc/tile_kernel.cuh``).
+
+Multi-rank decomposition (one process per GPU, ``torch.distributed`` / NCCL for plumbing only):
+rank r owns rows [r*n, (r+1)*n) of both modalities.  Forward: all-gather of the bf16-packed
+features, row-block tiles -> exact row LSE + per-column partial (max,sum) -> one small all-gather
+of those statistics.  Backward: two row passes, (I_r vs T_all) -> dI_r and (T_r vs I_all) -> dT_r,
+each complete on its own rank, so no gradient collective is needed at all: the reference's
+reduce-scatter of W full copies (torch/distributed/nn/functional.py:343-347) disappears.  The
+per-rank values reproduce the reference's conventions exactly:
+
+  (local_loss, gather_with_grad)   loss on rank r     d features                d logit_scale
+  (F, F)                           L_global           1/(2N) * (Pr + Pc - 2d)   global
+  (F, T)                           L_global           1/(2n) * (Pr + Pc - 2d)   global
+  (T, F)                           L_r                1/(2n) * (P_own - d)      local
+  (T, T)                           L_r                1/(2n) * (Pr + Pc - 2d)   local
+
+There is no CPU path: tensors must live on an sm_100a device, otherwise the call raises.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+try:
+    import torch.distributed.nn  # noqa: F401  (kept for parity with the reference's import guard)
+    from torch import distributed as dist
+    has_distributed = True
+except ImportError:  # pragma: no cover
+    dist = None
+    has_distributed = False
+
+from ._cabi import Shape
+from .engine import default_engine
+
+__all__ = ["ClipLoss", "SigLipLoss", "gather_features", "set_engine"]
+
+_engine_override = None
+
+
+def set_engine(engine):
+    """Test hook: route the device operations through ``engine`` (None restores the CUDA engine)."""
+    global _engine_override
+    _engine_override = engine
+
+
+def _engine():
+    return _engine_override if _engine_override is not None else default_engine()
+
+
+# --------------------------------------------------------------------------------------------
+# Differentiable gather with the reference's semantics (API parity for callers such as the
+# multi-positive subclasses; the fused losses below do not use it).
+# --------------------------------------------------------------------------------------------
+class _AllGatherWithGrad(torch.autograd.Function):
+    """all_gather whose backward is reduce_scatter(SUM), as torch.distributed.nn.all_gather."""
+
+    @staticmethod
+    def forward(ctx, x, world_size):
+        ctx.world_size = world_size
+        out = torch.empty((world_size * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x.contiguous())
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        n = grad.shape[0] // ctx.world_size
+        out = torch.empty((n,) + tuple(grad.shape[1:]), dtype=grad.dtype, device=grad.device)
+        dist.reduce_scatter_tensor(out, grad.contiguous(), op=dist.ReduceOp.SUM)
+        return out, None
+
+
+def gather_features(image_features, text_features, local_loss=False, gather_with_grad=False, rank=0,
+                    world_size=1, use_horovod=False):
+    """Reference ``gather_features`` (loss.py:21-65): rank-ordered concatenation of every rank's features."""
+    assert has_distributed, 'torch.distributed did not import correctly, please use a PyTorch version with support.'
+    if use_horovod:
+        raise NotImplementedError("Horovod is not supported by mrclip_b200 (NCCL over NVLink only)")
+    if gather_with_grad:
+        all_image_features = _AllGatherWithGrad.apply(image_features, world_size)
+        all_text_features = _AllGatherWithGrad.apply(text_features, world_size)
+    else:
+        with torch.no_grad():
+            all_image_features = _AllGatherWithGrad.apply(image_features, world_size)
+            all_text_features = _AllGatherWithGrad.apply(text_features, world_size)
+        if not local_loss:
+            # keep the graph for the local slot (loss.py:58-61)
+            n = image_features.shape[0]
+            parts_i = list(all_image_features.split(n, dim=0))
+            parts_t = list(all_text_features.split(n, dim=0))
+            parts_i[rank] = image_features
+            parts_t[rank] = text_features
+            all_image_features = torch.cat(parts_i, dim=0)
+            all_text_features = torch.cat(parts_t, dim=0)
+    return all_image_features, all_text_features
+
+
+# --------------------------------------------------------------------------------------------
+# Workspace: gathered bf16 operands, their transposes and the kernel scratch, reused across steps
+# --------------------------------------------------------------------------------------------
+class _Workspace:
+    def __init__(self, eng, device, n, world, d):
+        self.n, self.world, self.d = n, world, d
+        self.N = n * world
+        self.ld = eng.padded_dim(d)
+        self.npad = eng.padded_cols(self.N)
+        bf, f32 = torch.bfloat16, torch.float32
+        self.img_all = torch.zeros((self.N, self.ld), dtype=bf, device=device)
+        self.txt_all = torch.zeros((self.N, self.ld), dtype=bf, device=device)
+        self.img_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
+        self.txt_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
+        self.scratch = torch.empty(max(int(eng.workspace_bytes(n, self.N, d)), 256), dtype=torch.uint8, device=device)
+        # statistics in log2 units
+        self.stats_local = torch.zeros((3, self.N), dtype=f32, device=device)      # col_m, col_l, (row lse2 in [:n])
+        self.stats_all = torch.zeros((world, 3, self.N), dtype=f32, device=device) if world > 1 else None
+        self.lse2_row_all = torch.full((self.npad,), float("inf"), dtype=f32, device=device)
+        self.lse2_col_all = torch.full((self.npad,), float("inf"), dtype=f32, device=device)
+        self.diag2 = torch.zeros((n,), dtype=f32, device=device)
+        self.in_use = False
+        self.transposed = False
+
+
+class _WorkspacePool:
+    """Per-module cache keyed by (device, n, world, d); a set is handed out once until backward returns it."""
+
+    def __init__(self):
+        self._free = {}
+
+    def take(self, eng, device, n, world, d):
+        key = (str(device), n, world, d)
+        lst = self._free.setdefault(key, [])
+        for w in lst:
+            if not w.in_use:
+                w.in_use = True
+                w.transposed = False
+                return w
+        w = _Workspace(eng, device, n, world, d)
+        w.in_use = True
+        if len(lst) < 4:
+            lst.append(w)
+        return w
+
+    @staticmethod
+    def give_back(w):
+        w.in_use = False
+
+
+def _scalar_f32(x, device):
+    if torch.is_tensor(x):
+        return x.detach().reshape(-1)[:1].to(device=device, dtype=torch.float32).contiguous()
+    return torch.tensor([float(x)], dtype=torch.float32, device=device)
+
+
+def _check_inputs(image_features, text_features):
+    if image_features.dim() != 2 or image_features.shape != text_features.shape:
+        raise ValueError(f"expected two [n, D] feature matrices of equal shape, got {tuple(image_features.shape)} "
+                         f"and {tuple(text_features.shape)}")
+    if image_features.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise TypeError(f"unsupported feature dtype {image_features.dtype}")
+    if image_features.shape[0] == 0:
+        raise ValueError("empty batch")
+
+
+def _gather_packed(eng, ws, image_features, text_features, rank, world):
+    """Pack the local features to bf16 straight into their slot and all-gather in place."""
+    n = ws.n
+    rows = slice(rank * n, (rank + 1) * n)
+    img = image_features.detach()
+    txt = text_features.detach()
+    if img.stride(1) != 1:
+        img = img.contiguous()
+    if txt.stride(1) != 1:
+        txt = txt.contiguous()
+    eng.pack(img, ws.img_all[rows])
+    eng.pack(txt, ws.txt_all[rows])
+    if world > 1:
+        _all_gather_rows(ws.img_all, rows)
+        _all_gather_rows(ws.txt_all, rows)
+
+
+def _all_gather_rows(buf, rows):
+    """All-gather the [n, ld] slot ``buf[rows]`` of every rank into ``buf`` (in place on NCCL)."""
+    src = buf[rows]
+    if not buf.is_cuda:
+        src = src.clone()  # gloo (CPU tests) does not promise in-place semantics
+    dist.all_gather_into_tensor(buf, src)
+
+
+def _ensure_transposed(eng, ws):
+    if not ws.transposed:
+        eng.transpose(ws.img_all, ws.img_t)
+        eng.transpose(ws.txt_all, ws.txt_t)
+        ws.transposed = True
+
+
+class _ClipLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, module):
+        eng = _engine()
+        _check_inputs(image_features, text_features)
+        device = image_features.device
+        n, d = image_features.shape
+        world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
+        ws = module._pool.take(eng, device, n, world, d)
+        N = ws.N
+        scale = _scalar_f32(logit_scale, device)
+        shape = Shape(n, N, d, rank * n)
+        rows = slice(rank * n, (rank + 1) * n)
+
+        _gather_packed(eng, ws, image_features, text_features, rank, world)
+        eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
+        col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
+        eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
+        if world > 1:
+            dist.all_gather_into_tensor(ws.stats_all.view(world * 3, N), ws.stats_local)
+            eng.lse2_merge(ws.stats_all[0, 0], ws.stats_all[0, 1], world, 3 * N, N, ws.lse2_col_all)
+            ws.lse2_row_all[:N].view(world, n).copy_(ws.stats_all[:, 2, :n])
+        else:
+            eng.lse2_merge(col_m, col_l, 1, N, N, ws.lse2_col_all)
+            ws.lse2_row_all[:N].copy_(row_lse)
+        loss = torch.empty((1,), dtype=torch.float32, device=device)
+        eng.clip_loss(ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2, n, rank * n, loss)
+        if world > 1 and not module.local_loss:
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM)
+            loss /= world
+
+        ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+        ctx.scale = scale
+        ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+        ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+        if not any(ctx.needs_input_grad):
+            module._pool.give_back(ws)   # inference / no_grad: nothing will come back for these buffers
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        eng = _engine()
+        ws, module = ctx.ws, ctx.module
+        n, N, d, rank, world = ctx.shape_args
+        device = ws.img_all.device
+        rows = slice(rank * n, (rank + 1) * n)
+        shape = Shape(n, N, d, rank * n)
+        gout = grad_output.detach().reshape(1).to(torch.float32).contiguous()
+        if world > 1 and not module.local_loss and not module.gather_with_grad:
+            coef = 0.5 / N          # only the re-inserted local slot carries gradient (loss.py:58-61)
+        else:
+            coef = 0.5 / n          # 1/(2n): W x the global-mean gradient, or the local loss itself
+        w_oth = 0.0 if (world > 1 and module.local_loss and not module.gather_with_grad) else 1.0
+
+        _ensure_transposed(eng, ws)
+        need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_img = d_txt = d_scale = None
+        ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
+        # d logit_scale always uses 1/(2n) per rank; global modes average it over ranks below
+        if need_i or need_s:
+            d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+            eng.clip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ws.lse2_row_all[rows], ws.lse2_col_all,
+                         ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_img, ds, True)
+        if need_t or need_s:
+            d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
+            eng.clip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
+                         ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_txt, ds, True)
+        if need_s:
+            if coef != 0.5 / n:
+                ds *= (0.5 / n) / coef
+            if world > 1 and not module.local_loss:
+                dist.all_reduce(ds, op=dist.ReduceOp.SUM)
+                ds /= world
+            shp, dt = ctx.scale_meta
+            d_scale = ds.reshape(shp).to(dt)
+        module._pool.give_back(ws)
+        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None
+
+
+class ClipLoss(nn.Module):
+    """Reference ``ClipLoss`` (loss.py:68-139) on the fused sm_100a path."""
+
+    def __init__(self, local_loss=False, gather_with_grad=False, cache_labels=False, rank=0, world_size=1,
+                 use_horovod=False):
+        super().__init__()
+        if use_horovod:
+            raise NotImplementedError("Horovod is not supported by mrclip_b200 (NCCL over NVLink only)")
+        self.local_loss = local_loss
+        self.gather_with_grad = gather_with_grad
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.use_horovod = use_horovod
+
+        # cache state
+        self.prev_num_logits = 0
+        self.labels = {}
+        self._pool = _WorkspacePool()
+
+    def get_ground_truth(self, device, num_logits) -> torch.Tensor:
+        """loss.py:91-102, bit-exact: arange (+ num_logits*rank for local loss), cached per device."""
+        if self.prev_num_logits != num_logits or device not in self.labels:
+            labels = torch.arange(num_logits, device=device, dtype=torch.long)
+            if self.world_size > 1 and self.local_loss:
+                labels = labels + num_logits * self.rank
+            if self.cache_labels:
+                self.labels[device] = labels
+                self.prev_num_logits = num_logits
+        else:
+            labels = self.labels[device]
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale):
+        """Materialised logits (loss.py:104-126) for subclasses that need them (CoCa / distill / multi-positive).
+
+        Not used by ``forward``; plain tensor algebra with the reference's operand order.
+        """
+        if self.world_size > 1:
+            all_image_features, all_text_features = gather_features(
+                image_features, text_features, local_loss=self.local_loss, gather_with_grad=self.gather_with_grad,
+                rank=self.rank, world_size=self.world_size, use_horovod=self.use_horovod)
+            if self.local_loss:
+                logits_per_image = logit_scale * image_features @ all_text_features.T
+                logits_per_text = logit_scale * text_features @ all_image_features.T
+            else:
+                logits_per_image = logit_scale * all_image_features @ all_text_features.T
+                logits_per_text = logits_per_image.T
+        else:
+            logits_per_image = logit_scale * image_features @ text_features.T
+            logits_per_text = logit_scale * text_features @ image_features.T
+        return logits_per_image, logits_per_text
+
+    def forward(self, image_features, text_features, logit_scale, output_dict=False):
+        total_loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+class _SigLipLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, logit_bias, module):
+        eng = _engine()
+        _check_inputs(image_features, text_features)
+        device = image_features.device
+        n, d = image_features.shape
+        world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
+        ws = module._pool.take(eng, device, n, world, d)
+        N = ws.N
+        scale = _scalar_f32(logit_scale, device)
+        bias = _scalar_f32(logit_bias, device) if logit_bias is not None else None
+        shape = Shape(n, N, d, rank * n)
+        rows = slice(rank * n, (rank + 1) * n)
+        _gather_packed(eng, ws, image_features, text_features, rank, world)
+        loss = torch.empty((1,), dtype=torch.float32, device=device)
+        eng.siglip_fwd(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss)
+        ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+        ctx.scale, ctx.bias = scale, bias
+        ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+        ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+        ctx.bias_meta = (logit_bias.shape, logit_bias.dtype) if torch.is_tensor(logit_bias) else None
+        if not any(ctx.needs_input_grad):
+            module._pool.give_back(ws)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        eng = _engine()
+        ws, module = ctx.ws, ctx.module
+        n, N, d, rank, world = ctx.shape_args
+        device = ws.img_all.device
+        rows = slice(rank * n, (rank + 1) * n)
+        shape = Shape(n, N, d, rank * n)
+        gout = grad_output.detach().reshape(1).to(torch.float32).contiguous()
+        coef = 1.0 / n
+        _ensure_transposed(eng, ws)
+        need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        need_b = ctx.needs_input_grad[3] and ctx.bias_meta is not None
+        d_img = d_txt = d_scale = d_bias = None
+        ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
+        db = torch.zeros((1,), dtype=torch.float32, device=device) if need_b else None
+        if need_i or need_s or need_b:
+            d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+            eng.siglip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
+                           d_img, ds, db, False)
+        if need_t:
+            # every rank's loss touches T_r: the column block gives the summed (W x) gradient directly
+            d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
+            eng.siglip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
+                           d_txt, None, None, False)
+        if need_s:
+            shp, dt = ctx.scale_meta
+            d_scale = ds.reshape(shp).to(dt)
+        if need_b:
+            shp, dt = ctx.bias_meta
+            d_bias = db.reshape(shp).to(dt)
+        module._pool.give_back(ws)
+        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, d_bias, None
+
+
+class SigLipLoss(nn.Module):
+    """Reference ``SigLipLoss`` (loss.py:314-448).
+
+    All four ``dist_impl`` exchange schemes of the reference compute the same loss; on an NVSwitch
+    domain a single all-gather of the bf16 features replaces the W-1 neighbour hops, so ``dist_impl``
+    is validated and stored but does not change the communication pattern.
+    """
+
+    def __init__(self, cache_labels: bool = False, rank: int = 0, world_size: int = 1, dist_impl: Optional[str] = None):
+        super().__init__()
+        self.cache_labels = cache_labels
+        self.rank = rank
+        self.world_size = world_size
+        self.dist_impl = dist_impl or 'bidir'
+        assert self.dist_impl in ('bidir', 'shift', 'reduce', 'gather')
+
+        # cache state (unused, as in the reference)
+        self.prev_num_logits = 0
+        self.labels = {}
+        self._pool = _WorkspacePool()
+
+    def get_ground_truth(self, device, dtype, num_logits, negative_only=False) -> torch.Tensor:
+        """loss.py:338-342: -1 everywhere, +1 on the diagonal unless negative_only."""
+        labels = -torch.ones((num_logits, num_logits), device=device, dtype=dtype)
+        if not negative_only:
+            labels = 2 * torch.eye(num_logits, device=device, dtype=dtype) + labels
+        return labels
+
+    def get_logits(self, image_features, text_features, logit_scale, logit_bias=None):
+        """Materialised chunk logits (loss.py:344-348); not used by ``forward``."""
+        logits = logit_scale * image_features @ text_features.T
+        if logit_bias is not None:
+            logits = logits + logit_bias
+        return logits
+
+    def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict=False):
+        loss = _SigLipLossFn.apply(image_features, text_features, logit_scale, logit_bias, self)
+        return {"contrastive_loss": loss} if output_dict else loss

@@ -1,0 +1,188 @@
+"""Shared test plumbing: markers, golden-vector loader and the CPU stand-in engine.
+
+``-m "not gpu"`` tests run on the CPU-only build container; ``-m gpu`` tests need a B200 and go
+through the C ABI.  Nothing here reads /root/reference (it does not exist on the GPU box); the
+reference's outputs come from the committed fixtures in tests/golden/ (made by oracle/gen_golden.py).
+"""
+import glob
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (sm_100a) device; run with -m gpu on the GPU box")
+
+
+def golden_names(prefix=""):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN_DIR, prefix + "*.npz")))
+
+
+def load_golden(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    meta = {k[5:]: z[k].item() for k in z.files if k.startswith("meta_")}
+    world = int(meta["world"])
+    ranks = []
+    for r in range(world):
+        ranks.append({k[len(f"r{r}_"):]: z[k] for k in z.files if k.startswith(f"r{r}_")})
+    return dict(meta=meta, image=z["image"], text=z["text"], ranks=ranks, world=world)
+
+
+def rel_err(got, ref):
+    got = np.asarray(got, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    den = np.linalg.norm(ref.ravel())
+    return float(np.linalg.norm((got - ref).ravel()) / (den if den > 0 else 1.0))
+
+
+LOG2E = 1.4426950408889634
+
+
+class StandInEngine:
+    """CPU stand-in for ``mrclip_b200.engine.CudaEngine`` (tests only).
+
+    Implements the engine interface with dense float64 torch math so that the multi-rank
+    orchestration, the mode coefficients and the label logic in ``mrclip_b200/loss.py`` can be
+    exercised under gloo without a GPU.  It keeps per-scratch state in a dict instead of device
+    workspace.  The product never constructs this class.
+    """
+
+    name = "cpu-standin"
+
+    def __init__(self):
+        self.state = {}
+        self.calls = []
+
+    def padded_dim(self, d):
+        return (d + 7) // 8 * 8
+
+    def padded_cols(self, n):
+        return (n + 127) // 128 * 128
+
+    def workspace_bytes(self, m, n, d):
+        return 256
+
+    def fwd_col_granule(self, m, n):
+        return 128
+
+    def launch_count(self):
+        return len(self.calls)
+
+    def pack(self, src, dst):
+        self.calls.append("pack")
+        dst.zero_()
+        dst[:, :src.shape[1]] = src.to(torch.bfloat16)
+
+    def transpose(self, src, dst):
+        self.calls.append("transpose")
+        dst.zero_()
+        dst[:src.shape[1], :src.shape[0]] = src.t()
+
+    @staticmethod
+    def _cos(a_rows, b_all):
+        return a_rows.double() @ b_all.double().t()
+
+    def clip_fwd_tiles(self, a_rows, b_all, shape, scale, col_begin, col_end, ws):
+        self.calls.append("clip_fwd_tiles")
+        key = ws.data_ptr()
+        s = float(scale.item())
+        z = s * self._cos(a_rows, b_all)
+        st = self.state.setdefault(key, {})
+        st["z"] = z
+        st.setdefault("cols", set()).update(range(col_begin, col_end))
+
+    def clip_fwd_reduce(self, shape, ws, lse2_row, col_m, col_l, diag2):
+        self.calls.append("clip_fwd_reduce")
+        st = self.state.pop(ws.data_ptr())
+        assert st["cols"] == set(range(shape.n_cols)), "forward tiles did not cover every column"
+        z = st["z"]
+        lse2_row[:shape.m_rows] = (torch.logsumexp(z, dim=1) * LOG2E).float()
+        m = z.max(dim=0).values
+        col_m[:shape.n_cols] = (m * LOG2E).float()
+        col_l[:shape.n_cols] = torch.exp(z - m[None, :]).sum(dim=0).float()
+        idx = torch.arange(shape.m_rows)
+        diag2[:shape.m_rows] = (z[idx, idx + shape.label_offset] * LOG2E).float()
+
+    def lse2_merge(self, part_m, part_l, parts, stride, n_cols, out):
+        self.calls.append("lse2_merge")
+        ms = torch.as_strided(part_m, (parts, n_cols), (stride, 1)).double()
+        ls = torch.as_strided(part_l, (parts, n_cols), (stride, 1)).double()
+        mx = ms.max(dim=0).values
+        tot = (ls * torch.exp2(ms - mx[None, :])).sum(dim=0)
+        out.fill_(float("inf"))
+        out[:n_cols] = (mx + torch.log2(tot)).float()
+
+    def clip_loss(self, lse2_row, lse2_col, diag2, m_rows, label_offset, loss):
+        self.calls.append("clip_loss")
+        cols = lse2_col[label_offset:label_offset + m_rows].double()
+        tot = (lse2_row[:m_rows].double() + cols - 2 * diag2[:m_rows].double()).sum()
+        loss[0] = float(tot / LOG2E / (2 * m_rows))
+
+    def clip_bwd(self, a_rows, b_all, bt_all, shape, lse2_a, lse2_b, scale, w_own, w_oth, coef, grad_out, ws,
+                 d_a, d_scale, accumulate):
+        self.calls.append("clip_bwd")
+        s = float(scale.item())
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        cos = self._cos(a_rows, b_all)
+        assert torch.equal(bt_all[:b_all.shape[1], :b_all.shape[0]], b_all.t()), "stale transposed operand"
+        t2 = s * cos * LOG2E
+        p_own = torch.exp2(t2 - lse2_a[:shape.m_rows].double()[:, None])
+        p_oth = torch.exp2(t2 - lse2_b[:shape.n_cols].double()[None, :])
+        g = w_own * p_own + w_oth * p_oth
+        idx = torch.arange(shape.m_rows)
+        g[idx, idx + shape.label_offset] -= (w_own + w_oth)
+        d_a.copy_((coef * s * go * (g @ b_all.double()))[:, :d_a.shape[1]].to(d_a.dtype))
+        if d_scale is not None:
+            val = coef * go * w_own * ((p_own * cos).sum() - cos[idx, idx + shape.label_offset].sum())
+            d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + float(val)
+
+    def siglip_fwd(self, a_rows, b_all, shape, scale, bias, ws, loss):
+        self.calls.append("siglip_fwd")
+        s = float(scale.item())
+        b = 0.0 if bias is None else float(bias.item())
+        z = s * self._cos(a_rows, b_all) + b
+        y = -torch.ones_like(z)
+        idx = torch.arange(shape.m_rows)
+        y[idx, idx + shape.label_offset] = 1.0
+        loss[0] = float(torch.nn.functional.softplus(-y * z).sum() / shape.m_rows)
+
+    def siglip_bwd(self, a_rows, b_all, bt_all, shape, scale, bias, coef, grad_out, ws, d_a, d_scale, d_bias,
+                   accumulate):
+        self.calls.append("siglip_bwd")
+        s = float(scale.item())
+        b = 0.0 if bias is None else float(bias.item())
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        cos = self._cos(a_rows, b_all)
+        g = torch.sigmoid(s * cos + b)
+        idx = torch.arange(shape.m_rows)
+        g[idx, idx + shape.label_offset] -= 1.0
+        d_a.copy_((coef * s * go * (g @ b_all.double()))[:, :d_a.shape[1]].to(d_a.dtype))
+        if d_scale is not None:
+            d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + float(coef * go * (g * cos).sum())
+        if d_bias is not None:
+            d_bias[0] = (float(d_bias[0]) if accumulate else 0.0) + float(coef * go * g.sum())
+
+
+@pytest.fixture
+def standin_engine():
+    import mrclip_b200
+    eng = StandInEngine()
+    mrclip_b200.set_engine(eng)
+    yield eng
+    mrclip_b200.set_engine(None)
+
+
+def has_b200():
+    if not torch.cuda.is_available():
+        return False
+    return torch.cuda.get_device_capability(0)[0] == 10

@@ -1,0 +1,167 @@
+"""Host-side logic of mrclip_b200/loss.py on CPU: signatures, label cache, mode coefficients and the
+multi-rank orchestration (gloo, world_size 2 and 4), with the kernels replaced by the stand-in engine.
+
+Every expectation is the unmodified reference's output (tests/golden/)."""
+import inspect
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import mrclip_b200
+from conftest import StandInEngine, golden_names, load_golden, rel_err
+from mrclip_b200 import ClipLoss, SigLipLoss
+
+# stand-in math is float64 but features are packed to bf16 (exact for the fixtures) and grads are
+# returned in the input dtype (fp32)
+LOSS_TOL, GRAD_TOL = 5e-6, 5e-5
+
+
+def test_signatures_match_reference():
+    sig = inspect.signature(ClipLoss.__init__)
+    assert list(sig.parameters)[1:] == ["local_loss", "gather_with_grad", "cache_labels", "rank", "world_size",
+                                        "use_horovod"]
+    assert [p.default for p in list(sig.parameters.values())[1:]] == [False, False, False, 0, 1, False]
+    assert list(inspect.signature(ClipLoss.forward).parameters)[1:] == ["image_features", "text_features",
+                                                                        "logit_scale", "output_dict"]
+    assert list(inspect.signature(SigLipLoss.__init__).parameters)[1:] == ["cache_labels", "rank", "world_size",
+                                                                           "dist_impl"]
+    assert list(inspect.signature(SigLipLoss.forward).parameters)[1:] == ["image_features", "text_features",
+                                                                          "logit_scale", "logit_bias", "output_dict"]
+    assert list(inspect.signature(mrclip_b200.gather_features).parameters) == [
+        "image_features", "text_features", "local_loss", "gather_with_grad", "rank", "world_size", "use_horovod"]
+    with pytest.raises(AssertionError):
+        SigLipLoss(dist_impl="ring")
+    with pytest.raises(NotImplementedError):
+        ClipLoss(use_horovod=True)
+    with pytest.raises(TypeError):
+        ClipLoss()(torch.zeros(2, 2), torch.zeros(2, 2), 1.0, delta=0.5)   # reference raises TypeError too
+
+
+def test_label_cache_semantics():
+    dev = torch.device("cpu")
+    m = ClipLoss(local_loss=True, cache_labels=True, rank=3, world_size=4)
+    a = m.get_ground_truth(dev, 8)
+    assert a.dtype == torch.long and torch.equal(a, torch.arange(8) + 24)
+    assert m.get_ground_truth(dev, 8) is a and m.prev_num_logits == 8
+    b = m.get_ground_truth(dev, 4)
+    assert torch.equal(b, torch.arange(4) + 12) and m.prev_num_logits == 4
+    n = ClipLoss(local_loss=False, cache_labels=False, rank=3, world_size=4)
+    assert torch.equal(n.get_ground_truth(dev, 8), torch.arange(8)) and n.labels == {} and n.prev_num_logits == 0
+    s = SigLipLoss()
+    lab = s.get_ground_truth(dev, torch.float32, 3)
+    assert torch.equal(lab, 2 * torch.eye(3) - 1)
+    assert torch.equal(s.get_ground_truth(dev, torch.float32, 3, negative_only=True), -torch.ones(3, 3))
+
+
+def _run_rank(case, rank, world, img, txt):
+    m = case["meta"]
+    n = img.shape[0] // world
+    i_loc = torch.from_numpy(img[rank * n:(rank + 1) * n]).clone().requires_grad_(True)
+    t_loc = torch.from_numpy(txt[rank * n:(rank + 1) * n]).clone().requires_grad_(True)
+    scale = torch.tensor(float(m["scale"]), requires_grad=True)
+    out = {}
+    if m["kind"] == "clip":
+        mod = ClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
+                       cache_labels=True, rank=rank, world_size=world)
+        res = mod(i_loc, t_loc, scale, output_dict=True)
+        assert list(res) == ["contrastive_loss"]
+        loss = res["contrastive_loss"]
+        num_logits = n if (world > 1 and m["local_loss"]) else img.shape[0]
+        out["labels"] = mod.get_ground_truth(i_loc.device, num_logits).numpy()
+    else:
+        bias = torch.tensor(float(m["bias"]), requires_grad=True)
+        loss = SigLipLoss(rank=rank, world_size=world)(i_loc, t_loc, scale, bias)
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    (loss * float(m["grad_output"])).backward()
+    out.update(loss=loss.item(), d_image=i_loc.grad.numpy(), d_text=t_loc.grad.numpy(), d_scale=scale.grad.item())
+    if m["kind"] == "siglip":
+        out["d_bias"] = bias.grad.item()
+    return out
+
+
+def _compare(out, ref, kind):
+    assert abs(out["loss"] - float(ref["loss"])) <= LOSS_TOL * max(1.0, abs(float(ref["loss"])))
+    assert rel_err(out["d_image"], ref["d_image"]) <= GRAD_TOL
+    assert rel_err(out["d_text"], ref["d_text"]) <= GRAD_TOL
+    assert abs(out["d_scale"] - float(ref["d_scale"])) <= 1e-4 * max(abs(float(ref["d_scale"])), 1e-3)
+    if kind == "clip":
+        assert np.array_equal(out["labels"], ref["labels"])
+    else:
+        assert abs(out["d_bias"] - float(ref["d_bias"])) <= 1e-4 * max(abs(float(ref["d_bias"])), 1e-3)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "_w1" in n])
+def test_single_rank_matches_reference(name, standin_engine):
+    case = load_golden(name)
+    out = _run_rank(case, 0, 1, case["image"], case["text"])
+    _compare(out, case["ranks"][0], case["meta"]["kind"])
+    assert "clip_bwd" in standin_engine.calls or "siglip_bwd" in standin_engine.calls
+
+
+def _dist_worker(rank, world, init_file, name, ret):
+    mrclip_b200.set_engine(StandInEngine())
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        case = load_golden(name)
+        ret[rank] = _run_rank(case, rank, world, case["image"], case["text"])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+MULTI = [n for n in golden_names() if "_w1" not in n and "_w8" not in n]
+
+
+@pytest.mark.parametrize("name", MULTI)
+def test_multi_rank_gloo_matches_reference(name):
+    case = load_golden(name)
+    world = case["world"]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_dist_worker, args=(world, os.path.join(td, "init"), name, ret), nprocs=world, join=True)
+    for r in range(world):
+        _compare(ret[r], case["ranks"][r], case["meta"]["kind"])
+
+
+def _gather_worker(rank, world, init_file, ret):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(rank)
+        res = {}
+        for ll in (False, True):
+            for gg in (False, True):
+                a = torch.randn(3, 4, requires_grad=True)
+                b = torch.randn(3, 4, requires_grad=True)
+                ga, gb = mrclip_b200.gather_features(a, b, local_loss=ll, gather_with_grad=gg, rank=rank,
+                                                     world_size=world)
+                w = torch.arange(1, world * 3 + 1, dtype=torch.float32)[:, None]
+                (ga * w).sum().backward() if ga.requires_grad else None
+                res[(ll, gg)] = (ga.detach().numpy(), None if a.grad is None else a.grad.numpy())
+        ret[rank] = res
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_features_semantics_gloo():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_gather_worker, args=(world, os.path.join(td, "init"), ret), nprocs=world, join=True)
+    for r in range(world):
+        for (ll, gg), (ga, grad) in ret[r].items():
+            assert ga.shape == (6, 4)
+            w_rows = np.arange(1, 7, dtype=np.float32)[r * 3:(r + 1) * 3, None]
+            if gg:       # reduce-scatter of W identical weightings -> W x
+                assert np.allclose(grad, world * np.broadcast_to(w_rows, (3, 4)))
+            elif not ll:  # own slot re-inserted -> 1 x
+                assert np.allclose(grad, np.broadcast_to(w_rows, (3, 4)))
+            else:         # local loss without grad: gathered copy is detached
+                assert grad is None
