@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""bench.py -- ClipLoss fwd+bwd pairs/sec at global batch 32768, dim 768 (BASELINE.json config 3).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (port)
+
+N>1 is launched by torchrun (one rank per GPU, NCCL).  One "step" is one forward+backward of
+``ClipLoss(local_loss=True, gather_with_grad=True)`` over the rank's share of the global batch,
+through the public module (``mrclip_b200.ClipLoss``), collectives included.  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GLOBAL_BATCH = 32768
+DIM = 768
+LOGIT_SCALE = 14.285714
+METRIC = "ClipLoss fwd+bwd pairs/sec"
+UNIT = "pairs/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
+    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--feature-dtype", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(args):
+    return (f"ClipLoss local_loss=True gather_with_grad=True, global batch {args.global_batch}, dim {args.dim} "
+            f"(BASELINE.json configs[2])")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["bf16_tflops"]), float(j.get("bf16_tflops_sustained", j["bf16_tflops"])), "measured"
+    return 1590.0, 1400.0, "fallback"
+
+
+# ------------------------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from oracle.clip_port import time_clip_sample
+    res = time_clip_sample(args.global_batch, args.dim, args.cpu_sample_rows, steps=max(1, min(args.steps, 5)),
+                           warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": res["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "note": "reference algorithm on host cores (oracle/clip_port.py; "
+                   "the reference is pure PyTorch CPU code and /root/reference is absent on the GPU box)"},
+        "cpu_baseline": {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": res["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in out.strip().splitlines():
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        # the busiest samples are the ones under load
+        load = sorted(sm)[: max(1, len(sm))] if sm else []
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from mrclip_b200 import ClipLoss
+    from mrclip_b200.engine import default_engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    eng = default_engine()
+
+    N, D = args.global_batch, args.dim
+    assert N % world == 0
+    n = N // world
+    fdt = torch.bfloat16 if args.feature_dtype == "bf16" else torch.float32
+    g = torch.Generator().manual_seed(1234 + 3)
+    img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    txt = torch.nn.functional.normalize(0.5 * img + 0.5 * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
+    rows = slice(rank * n, (rank + 1) * n)
+    img_h = img[rows].to(fdt).contiguous().pin_memory()
+    txt_h = txt[rows].to(fdt).contiguous().pin_memory()
+    del img, txt
+    img_d = img_h.to(dev).requires_grad_(True)
+    txt_d = txt_h.to(dev).requires_grad_(True)
+    scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
+    loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+
+    def step(i, t):
+        i.grad = t.grad = scale.grad = None
+        loss = loss_mod(i, t, scale)
+        loss.backward()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step(img_d, txt_d)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count()
+    total_ms = timed(lambda: step(img_d, txt_d), args.steps)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    loss_val = float(step(img_d, txt_d).item())
+    ms_per_step = total_ms / args.steps
+    value = N / (ms_per_step * 1e-3)
+
+    # dominant kernel (backward row-pass tile kernel): CUDA events around each launch, live
+    ev = []
+    orig_bwd = eng.clip_bwd
+
+    def timed_bwd(*a, **k):
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        orig_bwd(*a, **k)
+        s1.record()
+        ev.append((s0, s1))
+
+    eng.clip_bwd = timed_bwd
+    for _ in range(min(args.steps, 10)):
+        step(img_d, txt_d)
+    torch.cuda.synchronize()
+    eng.clip_bwd = orig_bwd
+    kern_ms = statistics.mean(a.elapsed_time(b) for a, b in ev)
+    alg_flops_per_launch = 2.0 * n * N * D       # dA = G . B (one of the three algorithmic contractions)
+    burst, sustained, src = peaks()
+    achieved = alg_flops_per_launch / (kern_ms * 1e-3) / 1e12
+
+    # end to end: pinned host features -> device every step, loss read back every step
+    def e2e_step():
+        i = img_h.to(dev, non_blocking=True).requires_grad_(True)
+        t = txt_h.to(dev, non_blocking=True).requires_grad_(True)
+        return float(step(i, t).item())
+
+    for _ in range(2):
+        e2e_step()
+    e2e_ms = timed(e2e_step, args.steps) / args.steps
+    h2d = (img_h.numel() * img_h.element_size() + txt_h.numel() * txt_h.element_size())
+
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle.clip_port import time_clip_sample
+        res = time_clip_sample(N, D, args.cpu_sample_rows, steps=3, warmup=1)
+        cpu_base = {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                    "sample": res["sample"]}
+
+    if rank == 0:
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tp):
+            traffic = json.load(open(tp)).get("bwd_tile_kernel_dram_bytes_per_launch_at_bench_shape")
+        ws_mb = eng.workspace_bytes(n, N, D) / 2 ** 20
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": workload_name(args), "global_batch": N, "dim": D, "rows_per_gpu": n,
+                       "parallelism": f"dp{world}", "feature_dtype": args.feature_dtype, "logit_scale": LOGIT_SCALE,
+                       "l2": f"no flush: per-step working set (bf16 operands + {ws_mb:.0f} MiB workspace) exceeds the 126 MB L2",
+                       "loss": loss_val},
+            "algorithmic_tflops": 6.0 * N * N * D / world / (ms_per_step * 1e-3) / 1e12,
+            "frac_of_bf16_peak_per_gpu": 6.0 * N * N * D / world / (ms_per_step * 1e-3) / 1e12 / burst,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": burst, "unit": "TFLOP/s",
+                         "frac": achieved / burst, "traffic": traffic,
+                         "kernel": "tile_kernel<MODE_BWD> (row pass: S recompute + dA contraction)",
+                         "kernel_ms": kern_ms, "algorithmic_flops_per_launch": alg_flops_per_launch,
+                         "peak_source": f"{src} burst ({burst} TFLOP/s; sustained {sustained})",
+                         "frac_vs_sustained": achieved / sustained},
+            "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": e2e_ms},
+            "gpu_launches": launches,
+            "clocks": clocks,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

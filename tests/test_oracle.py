@@ -95,3 +95,37 @@ def test_cross_entropy_and_bf16_round():
     x = np.array([1.0, 1.00390625, 1.005859375, -3.1415927], dtype=np.float32)
     import torch
     assert np.array_equal(bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "_w1" in n])
+def test_timed_port_matches_reference(name):
+    """oracle/clip_port.py (the CPU baseline bench.py times) reproduces the reference's W=1 outputs."""
+    import torch
+    from oracle.clip_port import clip_rank_step, siglip_rank_step
+    g = load_golden(name)
+    m, ref = g["meta"], g["ranks"][0]
+    img, txt = torch.from_numpy(g["image"]), torch.from_numpy(g["text"])
+    if m["kind"] == "clip":
+        loss, di, dt, ds = clip_rank_step(img, txt, img, txt, float(m["scale"]), 0, float(m["grad_output"]))
+    else:
+        loss, di, dt, ds, db = siglip_rank_step(img, txt, float(m["scale"]), float(m["bias"]))
+        assert abs(db.item() - float(ref["d_bias"])) <= 1e-4 * abs(float(ref["d_bias"]))
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    assert rel_err(di.numpy(), ref["d_image"]) <= 1e-4 and rel_err(dt.numpy(), ref["d_text"]) <= 1e-4
+    assert abs(ds.item() - float(ref["d_scale"])) <= 1e-4 * abs(float(ref["d_scale"])) + 1e-6
+
+
+def test_timed_port_rank_block_matches_oracle():
+    import torch
+    from oracle.clip_port import clip_rank_step
+    rng = np.random.default_rng(3)
+    W, n, d = 4, 8, 16
+    img = rng.standard_normal((W * n, d)).astype(np.float32); img /= np.linalg.norm(img, axis=1, keepdims=True)
+    txt = rng.standard_normal((W * n, d)).astype(np.float32); txt /= np.linalg.norm(txt, axis=1, keepdims=True)
+    ref = clip_loss_oracle(_parts(img, W), _parts(txt, W), 10.0, True, False)
+    ti, tt = torch.from_numpy(img), torch.from_numpy(txt)
+    for r in range(W):
+        rows = slice(r * n, (r + 1) * n)
+        loss, di, dt, ds = clip_rank_step(ti[rows], tt[rows], ti, tt, 10.0, r * n)
+        assert abs(loss.item() - ref[r]["loss"]) < 1e-5
+        assert rel_err(di.numpy(), ref[r]["d_image"]) < 1e-5 and rel_err(dt.numpy(), ref[r]["d_text"]) < 1e-5
