@@ -176,7 +176,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // (the whole warp walks the loop so control flow stays uniform; one elected lane issues)
+    {
       uint32_t stage = 0, phase = 0;
       auto advance = [&]() {
         if (++stage == STAGES) {
@@ -190,10 +191,13 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         auto load_s = [&](int t) {
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(bar_empty(stage), phase ^ 1);
-            mbar_expect_tx(bar_full(stage), 2 * kBM * kBK * 2);
-            const uint32_t dst = stage_base + stage * kStageBytes;
-            tma_load_2d(dst, &tmA, bar_full(stage), kb * kBK, rb * kBM);
-            tma_load_2d(dst + kBM * kBK * 2, &tmB, bar_full(stage), kb * kBK, t * kBN);
+            if (elect_one()) {
+              mbar_expect_tx(bar_full(stage), 2 * kBM * kBK * 2);
+              const uint32_t dst = stage_base + stage * kStageBytes;
+              tma_load_2d(dst, &tmA, bar_full(stage), kb * kBK, rb * kBM);
+              tma_load_2d(dst + kBM * kBK * 2, &tmB, bar_full(stage), kb * kBK, t * kBN);
+            }
+            __syncwarp();
             advance();
           }
         };
@@ -201,9 +205,12 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kb2 = 0; kb2 < kBN / kBK; ++kb2) {
             for (int sub = 0; sub < NSUB; ++sub) {
               mbar_wait(bar_empty(stage), phase ^ 1);
-              mbar_expect_tx(bar_full(stage), DN * kBK * 2);
-              tma_load_2d(stage_base + stage * kStageBytes, &tmBt, bar_full(stage),
-                          t * kBN + kb2 * kBK, dc * DC + sub * DN);
+              if (elect_one()) {
+                mbar_expect_tx(bar_full(stage), DN * kBK * 2);
+                tma_load_2d(stage_base + stage * kStageBytes, &tmBt, bar_full(stage),
+                            t * kBN + kb2 * kBK, dc * DC + sub * DN);
+              }
+              __syncwarp();
               advance();
             }
           }
@@ -222,7 +229,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     __syncwarp();
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // (warp-uniform loop; tcgen05.mma / commit are issued by one elected lane)
+    {
       uint32_t stage = 0, phase = 0;
       auto advance = [&]() {
         if (++stage == STAGES) {
@@ -243,16 +251,21 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
             const uint32_t a = stage_base + stage * kStageBytes;
-            const uint32_t b = a + kBM * kBK * 2;
+            const uint64_t adesc = make_kmajor_sw128_desc(a);
+            const uint64_t bdesc = make_kmajor_sw128_desc(a + kBM * kBK * 2);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < kBK / 16; ++k) {
-              umma_bf16(d_tmem, make_kmajor_sw128_desc(a + k * 32), make_kmajor_sw128_desc(b + k * 32),
-                        IDESC_S, (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < kBK / 16; ++k) {
+                // +32 bytes per K=16 step inside the swizzle atom == +2 in the (addr >> 4) field
+                umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC_S, (kb | k) != 0 ? 1u : 0u);
+              }
+              umma_commit(bar_empty(stage));
             }
-            umma_commit(bar_empty(stage));
+            __syncwarp();
             advance();
           }
-          umma_commit(bar_sfull(buf));
+          if (elect_one()) umma_commit(bar_sfull(buf));
+          __syncwarp();
           ++s_use;
         };
         auto mma_d = [&](bool first) {
@@ -267,19 +280,22 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int sub = 0; sub < NSUB; ++sub) {
               mbar_wait(bar_full(stage), phase);
               tc_fence_after();
-              const uint32_t a = g_base + gb * 32768 + kb2 * 16384;
-              const uint32_t b = stage_base + stage * kStageBytes;
+              const uint64_t adesc = make_kmajor_sw128_desc(g_base + gb * 32768 + kb2 * 16384);
+              const uint64_t bdesc = make_kmajor_sw128_desc(stage_base + stage * kStageBytes);
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < kBK / 16; ++k) {
-                umma_bf16(tmem_base + Cfg::kDaCol + sub * DN, make_kmajor_sw128_desc(a + k * 32),
-                          make_kmajor_sw128_desc(b + k * 32), IDESC_D,
-                          (first && kb2 == 0 && k == 0) ? 0u : 1u);
+                for (int k = 0; k < kBK / 16; ++k) {
+                  umma_bf16(tmem_base + Cfg::kDaCol + sub * DN, adesc + 2 * k, bdesc + 2 * k, IDESC_D,
+                            (first && kb2 == 0 && k == 0) ? 0u : 1u);
+                }
+                umma_commit(bar_empty(stage));
               }
-              umma_commit(bar_empty(stage));
+              __syncwarp();
               advance();
             }
           }
-          umma_commit(bar_gempty(gb));
+          if (elect_one()) umma_commit(bar_gempty(gb));
+          __syncwarp();
           ++g_use;
         };
         if (MODE == MODE_FWD) {
@@ -290,7 +306,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (t + 1 < t1) mma_s();
             mma_d(t == t0);
           }
-          umma_commit(bar_dafull);
+          if (elect_one()) umma_commit(bar_dafull);
+          __syncwarp();
           ++item_count;
         }
       }
