@@ -101,6 +101,28 @@ int mrclip_siglip_bwd(const void* a_rows, const void* b_all, const void* bt_all,
                       const float* grad_out, void* ws, void* d_a, int out_dtype, long out_ld,
                       float* d_scale, float* d_bias, int accumulate_scalars, void* stream);
 
+/* ---- Backward through a materialised bf16 gradient block ("gmat" backend) ------------------------ */
+/* The fused row pass above needs no O(n*N) memory but recomputes S once per 384-wide slice of D (TMEM
+ * holds 512 fp32 columns).  When mrclip_gmat_bytes(m_rows, n_cols) of scratch is affordable this trio is
+ * faster: S is recomputed once, G = dLoss/dS is written as bf16 [m_pad, padded_cols(n_cols)], and each
+ * gradient is one plain tcgen05 GEMM against it. */
+size_t mrclip_gmat_bytes(int m_rows, int n_cols);
+/* G_ij as in mrclip_clip_bwd (unscaled); d_scale as in mrclip_clip_bwd; with both_directions != 0 the
+ * other-direction term  coef*grad_out*w_oth*(sum exp(S_ij - lse_b_j) C_ij - sum C_ii)  is added as well
+ * (world_size 1, where one G block serves both gradients). */
+int mrclip_clip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* lse2_a,
+                       const float* lse2_b, const float* scale, float w_own, float w_oth, float coef,
+                       const float* grad_out, void* ws, void* gmat, float* d_scale, int accumulate_scalars,
+                       int both_directions, void* stream);
+int mrclip_siglip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                         const float* bias, float coef, const float* grad_out, void* ws, void* gmat, float* d_scale,
+                         float* d_bias, int accumulate_scalars, void* stream);
+/* transposed == 0: d_out[m_rows, d] = coef*scale*grad_out * G . B      (bt = B^T, [ld, bt_ld >= n_cols])
+ * transposed != 0: d_out[n_cols, d] = coef*scale*grad_out * G^T . A    (bt = A^T, [ld, bt_ld >= m_rows]) */
+int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* bt, long bt_ld, int ld, float coef,
+                     const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
+                     void* stream);
+
 /* number of kernels this library has launched on behalf of the calling process (for bench accounting) */
 long mrclip_launch_count(void);
 

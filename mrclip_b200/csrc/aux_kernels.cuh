@@ -133,7 +133,7 @@ __global__ void clip_loss_kernel(const float* __restrict__ lse2_row, const float
 __global__ void scalar_reduce_kernel(const float2* __restrict__ part, long count, float cx, float cy,
                                      const float* __restrict__ mul_dev, const float* __restrict__ mul_dev2,
                                      float* __restrict__ out_x, float* __restrict__ out_y,
-                                     int accumulate) {
+                                     int accumulate, int fold_y_into_x) {
   __shared__ double rx[32], ry[32];
   double ax = 0.0, ay = 0.0;
   for (long i = threadIdx.x; i < count; i += blockDim.x) {
@@ -159,8 +159,12 @@ __global__ void scalar_reduce_kernel(const float2* __restrict__ part, long count
     double mul = 1.0;
     if (mul_dev) mul *= (double)mul_dev[0];
     if (mul_dev2) mul *= (double)mul_dev2[0];
-    if (out_x) out_x[0] = (accumulate ? out_x[0] : 0.f) + (float)(tx * cx * mul);
-    if (out_y) out_y[0] = (accumulate ? out_y[0] : 0.f) + (float)(ty * cy * mul);
+    if (fold_y_into_x) {
+      if (out_x) out_x[0] = (accumulate ? out_x[0] : 0.f) + (float)((tx * cx + ty * cy) * mul);
+    } else {
+      if (out_x) out_x[0] = (accumulate ? out_x[0] : 0.f) + (float)(tx * cx * mul);
+      if (out_y) out_y[0] = (accumulate ? out_y[0] : 0.f) + (float)(ty * cy * mul);
+    }
   }
 }
 

@@ -2,6 +2,7 @@
 // carving) and kernel launches.  See include/mrclip.h for the contract.
 #include "../../include/mrclip.h"
 #include "aux_kernels.cuh"
+#include "gemm_kernel.cuh"
 #include "tile_kernel.cuh"
 
 #include <atomic>
@@ -69,6 +70,7 @@ EncodeTiledFn encode_fn() {
 
 // bf16 matrix [rows, cols] with row stride ld elements; box = [box_rows, 64 cols], 128B swizzle
 int make_map(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
+  // box is always 64 elements (128 bytes) wide: one swizzle row
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld * 2) % 16 != 0)
@@ -140,6 +142,39 @@ BwdPlan bwd_plan(int m_rows, int n_cols, int ld) {
   return b;
 }
 
+struct GemmPlan {
+  int num_rb, num_dt, num_kb, ksplit, kb_per_split, num_items, m_pad, d_pad;
+};
+// out_rows = rows of the gradient being produced, k_len = length of the contraction
+GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
+  GemmPlan g;
+  g.num_rb = ceil_div(out_rows, kBM);
+  g.num_dt = ceil_div(ld, kGemmBN);
+  g.num_kb = ceil_div(k_len, kBK);
+  g.m_pad = g.num_rb * kBM;
+  g.d_pad = g.num_dt * kGemmBN;
+  const int sms = num_sms();
+  const int base = g.num_rb * g.num_dt;
+  int best = 1;
+  double best_eff = 0.0;
+  for (int ks = 1; ks <= 16; ++ks) {
+    const int per = ceil_div(g.num_kb, ks);
+    if (ks > 1 && per < 16) break;
+    const int ks_eff = ceil_div(g.num_kb, per);
+    const long items = (long)base * ks_eff;
+    const double eff = (double)items / ((double)ceil_div((int)items, sms) * sms);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best = ks_eff;
+    }
+    if (best_eff >= 0.95) break;
+  }
+  g.kb_per_split = ceil_div(g.num_kb, best);
+  g.ksplit = ceil_div(g.num_kb, g.kb_per_split);
+  g.num_items = base * g.ksplit;
+  return g;
+}
+
 struct WsLayout {
   size_t row_part, col_l, col_c, diag2, sc_part, dpart, total;
 };
@@ -161,7 +196,15 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   const size_t fwd_end = off;
   // backward view (aliases the forward view; forward partials are dead by then)
   w.dpart = 0;
-  const size_t bwd_end = align_up((size_t)b.cs * b.m_pad * b.d_pad * sizeof(float), 256);
+  size_t bwd_end = align_up((size_t)b.cs * b.m_pad * b.d_pad * sizeof(float), 256);
+  {
+    const GemmPlan g1 = gemm_plan(m_rows, n_cols, ld);   // dA = G . Bt      (contraction over columns)
+    const GemmPlan g2 = gemm_plan(n_cols, m_rows, ld);   // dB = G^T . At    (contraction over rows)
+    const size_t e1 = align_up((size_t)g1.ksplit * g1.m_pad * g1.d_pad * sizeof(float), 256);
+    const size_t e2 = align_up((size_t)g2.ksplit * g2.m_pad * g2.d_pad * sizeof(float), 256);
+    if (e1 > bwd_end) bwd_end = e1;
+    if (e2 > bwd_end) bwd_end = e2;
+  }
   off = fwd_end > bwd_end ? fwd_end : bwd_end;
   w.sc_part = off;
   const size_t items_f = (size_t)f.num_rb * f.total_chunks;
@@ -302,10 +345,118 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
   if (d_scale || d_bias) {
     const float cx = coef * (loss_kind == LOSS_CLIP ? w_own : 1.f);
     scalar_reduce_kernel<<<1, 1024, 0, st>>>(p.sc_part, (long)b.num_items * kEpiWarps, cx, coef, grad_out,
-                                             nullptr, d_scale, d_bias, accumulate);
+                                             nullptr, d_scale, d_bias, accumulate, 0);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
   }
+  return 0;
+}
+
+template <bool A_MN>
+int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_kernel<A_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes));
+    attr_set = true;
+  }
+  int grid = p.num_items < num_sms() ? p.num_items : num_sms();
+  if (const char* g = getenv("MRCLIP_GRID")) {
+    const int cap = atoi(g);
+    if (cap > 0 && cap < grid) grid = cap;
+  }
+  if (grid <= 0) return 0;
+  kern<<<grid, kThreads, kGemmSmemBytes, st>>>(ma, mb, p);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+// Recompute S for this rank's row block and write G = dLoss/dS (bf16, unscaled) to gmat [m_pad, n_pad].
+int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
+               const float* lse2_a, const float* lse2_b, const float* scale, const float* bias, float w_own,
+               float w_oth, void* ws, void* gmat, cudaStream_t st) {
+  if (int e = check_shape(sh, ld)) return e;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  CUtensorMap ma, mb;
+  if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kBN)) return e;
+  TileParams p;
+  memset(&p, 0, sizeof p);
+  p.m_rows = sh.m_rows;
+  p.n_cols = sh.n_cols;
+  p.num_kb = ceil_div(ld, kBK);
+  p.num_rb = f.num_rb;
+  p.tile_begin = 0;
+  p.tile_end = f.num_ct;
+  p.tiles_per_chunk = f.tiles_per_chunk;
+  p.num_chunks = f.total_chunks;
+  p.chunk_base = 0;
+  p.num_dc = 1;
+  p.num_items = f.total_chunks * f.num_rb;
+  p.label_offset = sh.label_offset;
+  p.m_pad = f.m_pad;
+  p.n_pad = f.n_pad;
+  p.scale = scale;
+  p.bias = bias;
+  p.w_own = w_own;
+  p.w_oth = w_oth;
+  p.lse2_a = lse2_a;
+  p.lse2_b = lse2_b;
+  p.g_out = reinterpret_cast<uint16_t*>(gmat);
+  p.g_ld = f.n_pad;
+  p.sc_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part);
+  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_GW, LOSS_CLIP, 256>(ma, mb, mb, p, st);
+  return launch_tile<MODE_GW, LOSS_SIGLIP, 256>(ma, mb, mb, p, st);
+}
+
+// d_out[out_rows, d] = mul * sum_k G(.,.) * Bt[d, k]; transposed=false contracts G's columns (out rows = G rows),
+// transposed=true contracts G's rows (out rows = G columns; G read as an MN-major operand).
+int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* bt, long bt_ld, int d, int ld,
+                  float coef, const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype,
+                  long out_ld, cudaStream_t st) {
+  const int out_rows = transposed ? g_cols : g_rows;
+  const int k_len = transposed ? g_rows : g_cols;
+  const GemmPlan g = gemm_plan(out_rows, k_len, ld);
+  const long g_ld = mrclip_padded_cols(g_cols);
+  if (bt_ld < k_len || bt_ld % 8 != 0) return fail(-1, "bt_ld=%ld must be a multiple of 8 and >= %d", bt_ld, k_len);
+  CUtensorMap ma, mb;
+  if (int e = make_map(&ma, gmat, g_rows, g_cols, g_ld, transposed ? 64 : kBM)) return e;
+  if (int e = make_map(&mb, bt, ld, k_len, bt_ld, kGemmBN)) return e;
+  GemmParams p;
+  memset(&p, 0, sizeof p);
+  p.m_rows = out_rows;
+  p.num_rb = g.num_rb;
+  p.num_dt = g.num_dt;
+  p.num_kb = g.num_kb;
+  p.kb_per_split = g.kb_per_split;
+  p.ksplit = g.ksplit;
+  p.num_items = g.num_items;
+  p.m_pad = g.m_pad;
+  p.d_pad = g.d_pad;
+  p.dpart = reinterpret_cast<float*>(ws);
+  if (int e = transposed ? launch_gemm<true>(ma, mb, p, st) : launch_gemm<false>(ma, mb, p, st)) return e;
+  const long total = (long)out_rows * (g.d_pad / 4);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  grad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.dpart, g.ksplit, out_rows, d, g.m_pad, g.d_pad, coef, scale,
+                                                   grad_out, d_out, out_dtype, out_ld);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int run_scalar_reduce(const mrclip_shape& sh, void* ws, float cx, float cy, const float* grad_out, float* d_scale,
+                      float* d_bias, int accumulate, int fold, cudaStream_t st) {
+  if (!d_scale && !d_bias) return 0;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  scalar_reduce_kernel<<<1, 1024, 0, st>>>(
+      reinterpret_cast<const float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part),
+      (long)f.num_rb * f.total_chunks * kEpiWarps, cx, cy, grad_out, nullptr, d_scale, d_bias, accumulate, fold);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
   return 0;
 }
 
@@ -432,7 +583,7 @@ int mrclip_siglip_fwd(const void* a_rows, const void* b_all, mrclip_shape shape,
   uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
   scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
                                            (long)f.num_rb * f.total_chunks * kEpiWarps,
-                                           1.f / (float)shape.m_rows, 0.f, nullptr, nullptr, loss, nullptr, 0);
+                                           1.f / (float)shape.m_rows, 0.f, nullptr, nullptr, loss, nullptr, 0, 0);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -445,6 +596,40 @@ int mrclip_siglip_bwd(const void* a_rows, const void* b_all, const void* bt_all,
   return run_bwd(LOSS_SIGLIP, a_rows, b_all, bt_all, bt_ld, shape, ld, nullptr, nullptr, scale, bias, 1.f, 0.f,
                  coef, grad_out, ws, d_a, out_dtype, out_ld, d_scale, d_bias, accumulate_scalars,
                  (cudaStream_t)stream);
+}
+
+size_t mrclip_gmat_bytes(int m_rows, int n_cols) {
+  if (m_rows <= 0 || n_cols <= 0) return 0;
+  return (size_t)ceil_div(m_rows, kBM) * kBM * (size_t)mrclip_padded_cols(n_cols) * 2;
+}
+
+int mrclip_clip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* lse2_a,
+                       const float* lse2_b, const float* scale, float w_own, float w_oth, float coef,
+                       const float* grad_out, void* ws, void* gmat, float* d_scale, int accumulate_scalars,
+                       int both_directions, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = run_gwrite(LOSS_CLIP, a_rows, b_all, shape, ld, lse2_a, lse2_b, scale, nullptr, w_own, w_oth, ws, gmat, st))
+    return e;
+  return run_scalar_reduce(shape, ws, coef * w_own, both_directions ? coef * w_oth : 0.f, grad_out, d_scale, nullptr,
+                           accumulate_scalars, 1, st);
+}
+
+int mrclip_siglip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                         const float* bias, float coef, const float* grad_out, void* ws, void* gmat, float* d_scale,
+                         float* d_bias, int accumulate_scalars, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = run_gwrite(LOSS_SIGLIP, a_rows, b_all, shape, ld, nullptr, nullptr, scale, bias, 1.f, 0.f, ws, gmat, st))
+    return e;
+  return run_scalar_reduce(shape, ws, coef, coef, grad_out, d_scale, d_bias, accumulate_scalars, 0, st);
+}
+
+int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* bt, long bt_ld, int ld, float coef,
+                     const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
+                     void* stream) {
+  if (int e = check_shape(shape, ld)) return e;
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, bt, bt_ld, shape.d, ld, coef, scale, grad_out,
+                       ws, d_out, out_dtype, out_ld, (cudaStream_t)stream);
 }
 
 }  // extern "C"

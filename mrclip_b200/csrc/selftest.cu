@@ -263,6 +263,41 @@ static void check_clip(int N, int D, int W, float s, float corr) {
   report("dT", rel_err(dT, hT), 1e-2);
   report("d_scale per rank", rel_err(dS, hds), 1e-2);
   printf("    ds[0] = %.6e (ref %.6e)\n", hds[0], dS[0]);
+  // ---- gmat backend: G written once per pass, gradients as plain GEMMs
+  {
+    void* gmat;
+    CK(cudaMalloc(&gmat, mrclip_gmat_bytes(n, N)));
+    CK(cudaMemset(gmat, 0xff, mrclip_gmat_bytes(n, N)));
+    for (int r = 0; r < W; ++r) {
+      mrclip_shape sh = {n, N, D, r * n};
+      const char* ai = (const char*)d.Ibf + (size_t)r * n * d.ld * 2;
+      const char* at = (const char*)d.Tbf + (size_t)r * n * d.ld * 2;
+      MR(mrclip_clip_gwrite(ai, d.Tbf, sh, d.ld, lse2_row_all + r * n, lse2_col_all, d.scale, 1.f, 1.f, (float)coef,
+                            d.gout, d.ws, gmat, dscale + r, 0, W == 1 ? 1 : 0, 0));
+      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tt, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws,
+                          dA + (size_t)r * n * D, MRCLIP_DT_F32, D, 0));
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(hI.data() + (size_t)r * n * D, dA + (size_t)r * n * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost));
+      if (W == 1) {
+        MR(mrclip_gmat_gemm(1, gmat, sh, d.It, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hT.data(), dA, (size_t)N * D * 4, cudaMemcpyDeviceToHost));
+        report("gmat dT (transposed G)", rel_err(dT, hT), 1e-2);
+      } else {
+        MR(mrclip_clip_gwrite(at, d.Ibf, sh, d.ld, lse2_col_all + r * n, lse2_row_all, d.scale, 1.f, 1.f, (float)coef,
+                              d.gout, d.ws, gmat, dscale + r, 1, 0, 0));
+        MR(mrclip_gmat_gemm(0, gmat, sh, d.It, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws,
+                            dA + (size_t)r * n * D, MRCLIP_DT_F32, D, 0));
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(hT.data() + (size_t)r * n * D, dA + (size_t)r * n * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost));
+      }
+    }
+    CK(cudaMemcpy(hds.data(), dscale, W * 4, cudaMemcpyDeviceToHost));
+    report("gmat dI", rel_err(dI, hI), 1e-2);
+    if (W > 1) report("gmat dT (column pass)", rel_err(dT, hT), 1e-2);
+    report("gmat d_scale per rank", rel_err(dS, hds), 1e-2);
+    cudaFree(gmat);
+  }
   cudaFree(lse2_row_all); cudaFree(col_m); cudaFree(col_l); cudaFree(lse2_col_all); cudaFree(diag2);
   cudaFree(loss); cudaFree(dscale); cudaFree(dA);
   teardown(d);
@@ -397,6 +432,34 @@ static void time_shape(int N, int D, int reps) {
   printf("  loss %.5f | fwd %.3f ms (%.0f TF/s exec) | bwd passes %.3f + %.3f ms | total %.3f ms -> %.2f Mpairs/s, %.1f TF/s algorithmic (6N^2D)\n",
          hl, tf, flop / tf * 1e-9, tb1, tb2, tf + tb1 + tb2, N / (tf + tb1 + tb2) * 1e-3,
          3 * flop / (tf + tb1 + tb2) * 1e-9);
+  {
+    void* gmat;
+    CK(cudaMalloc(&gmat, mrclip_gmat_bytes(N, N)));
+    cudaEvent_t g0, g1, g2, g3;
+    cudaEventCreate(&g0); cudaEventCreate(&g1); cudaEventCreate(&g2); cudaEventCreate(&g3);
+    float ta = 0, tb = 0, tc = 0;
+    for (int it = 0; it < reps + 2; ++it) {
+      CK(cudaEventRecord(g0));
+      MR(mrclip_clip_gwrite(d.Ibf, d.Tbf, sh, d.ld, lse2_row, lse2_col, d.scale, 1.f, 1.f, 0.5f / N, d.gout, d.ws, gmat,
+                            dscale, 0, 1, 0));
+      CK(cudaEventRecord(g1));
+      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tt, d.npad, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+      CK(cudaEventRecord(g2));
+      MR(mrclip_gmat_gemm(1, gmat, sh, d.It, d.npad, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+      CK(cudaEventRecord(g3));
+      CK(cudaEventSynchronize(g3));
+      float a, b, c;
+      cudaEventElapsedTime(&a, g0, g1);
+      cudaEventElapsedTime(&b, g1, g2);
+      cudaEventElapsedTime(&c, g2, g3);
+      if (it >= 2) { ta += a; tb += b; tc += c; }
+    }
+    ta /= reps; tb /= reps; tc /= reps;
+    printf("  gmat: gwrite %.3f ms | gemm %.3f ms (%.0f TF/s) | gemm^T %.3f ms | fwd+gmat total %.3f ms -> %.2f Mpairs/s, %.1f TF/s algorithmic\n",
+           ta, tb, flop / tb * 1e-9, tc, tf + ta + tb + tc, N / (tf + ta + tb + tc) * 1e-3,
+           3 * flop / (tf + ta + tb + tc) * 1e-9);
+    cudaFree(gmat);
+  }
   teardown(d);
 }
 

@@ -32,7 +32,7 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum : int { MODE_FWD = 0, MODE_BWD = 1 };
+enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2 };  // GW: recompute S, write the bf16 gradient tile G to global
 enum : int { LOSS_CLIP = 0, LOSS_SIGLIP = 1 };
 
 struct TileParams {
@@ -63,6 +63,9 @@ struct TileParams {
   const float* lse2_a;  // [m_rows]   own-direction LSE of each A row (log2 units)
   const float* lse2_b;  // [n_pad]    other-direction LSE of each B row, +inf padded
   float* dpart;         // [cs][m_pad][d_pad]
+  // GW
+  uint16_t* g_out;      // bf16 [m_pad][g_ld]
+  long g_ld;
 };
 
 template <int LEN, int OFF>
@@ -85,12 +88,13 @@ __device__ __forceinline__ float log1p_from_exp(float e) {
 
 template <int MODE, int LOSS, int DC>
 struct TileCfg {
-  static constexpr int kSBufs = (MODE == MODE_FWD) ? 2 : (DC == 256 ? 2 : 1);
-  static constexpr int kTmemCols = (MODE == MODE_FWD) ? 256 : 512;
+  static constexpr bool kHasDa = (MODE == MODE_BWD);   // second GEMM fused in the same kernel
+  static constexpr int kSBufs = (!kHasDa) ? 2 : (DC == 256 ? 2 : 1);
+  static constexpr int kTmemCols = (!kHasDa) ? 256 : 512;
   static constexpr int kDaCol = kSBufs * kBN;
   static constexpr int kNSub = (DC == 384) ? 2 : 1;
   static constexpr int kDN = DC / kNSub;
-  static constexpr int kStages = (MODE == MODE_FWD) ? 6 : 5;
+  static constexpr int kStages = (!kHasDa) ? 6 : 5;
   static constexpr int kGBytes = (MODE == MODE_BWD) ? 2 * 32768 : 0;
   static constexpr int kNumBars = 2 * kStages + 10;
   static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kNumBars * 8 + 16 + 1024;
@@ -215,7 +219,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
         };
-        if (MODE == MODE_FWD) {
+        if (!Cfg::kHasDa) {
           for (int t = t0; t < t1; ++t) load_s(t);
         } else {
           load_s(t0);
@@ -298,7 +302,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           __syncwarp();
           ++g_use;
         };
-        if (MODE == MODE_FWD) {
+        if (!Cfg::kHasDa) {
           for (int t = t0; t < t1; ++t) mma_s();
         } else {
           mma_s();
@@ -336,7 +340,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float m_run = -CUDART_INF_F, l_run = 0.f;  // FWD clip: running row (max2, sum)
       float acc0 = 0.f, acc1 = 0.f;              // scalar partials (loss | ds, db)
       float lr2 = CUDART_INF_F;
-      if (MODE == MODE_BWD && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
+      if (MODE != MODE_FWD && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
 
       for (int t = t0; t < t1; ++t) {
         const uint32_t buf = s_use % NSB, use = s_use / NSB;
@@ -425,11 +429,12 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
           if (row_valid) acc0 += part;
         } else {
-          // ------------------------------------------------------------- BWD: build G
+          // ------------------------------------------------------------- BWD / GW: build G
           const uint32_t gb = g_use & 1, guse = g_use >> 1;
-          mbar_wait(bar_gempty(gb), (guse & 1) ^ 1);
+          if (MODE == MODE_BWD) mbar_wait(bar_gempty(gb), (guse & 1) ^ 1);
           const uint32_t grow_smem =
               g_base + gb * 32768 + h * 16384 + row_in_tile * 128;
+          uint16_t* grow_gmem = (MODE == MODE_GW) ? p.g_out + (size_t)grow * p.g_ld + col_base : nullptr;
           float dsum = 0.f, bsum = 0.f;
 #pragma unroll
           for (int ck = 0; ck < 8; ++ck) {
@@ -448,6 +453,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float p_oth = ex2f(tt - lb[j]);
                 g[j] = p.w_own * p_own + p.w_oth * p_oth;
                 dsum = fmaf(p_own, a, dsum);
+                if (MODE == MODE_GW) bsum = fmaf(p_oth, a, bsum);   // other-direction term of d_scale
               }
             } else {
 #pragma unroll
@@ -480,6 +486,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   if (LOSS == LOSS_CLIP) {
                     g[j] -= (p.w_own + p.w_oth);
                     dsum -= a;
+                    if (MODE == MODE_GW) bsum -= a;
                   } else {
                     g[j] -= 1.f;
                     dsum -= a;
@@ -488,15 +495,26 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
               }
             }
-            const uint32_t dst = grow_smem + ((static_cast<uint32_t>(ck) ^ (row_in_tile & 7)) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
-                         "r"(pack_bf16x2(g[0], g[1])), "r"(pack_bf16x2(g[2], g[3])),
-                         "r"(pack_bf16x2(g[4], g[5])), "r"(pack_bf16x2(g[6], g[7]))
-                         : "memory");
+            if (MODE == MODE_BWD) {
+              const uint32_t dst = grow_smem + ((static_cast<uint32_t>(ck) ^ (row_in_tile & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst),
+                           "r"(pack_bf16x2(g[0], g[1])), "r"(pack_bf16x2(g[2], g[3])),
+                           "r"(pack_bf16x2(g[4], g[5])), "r"(pack_bf16x2(g[6], g[7]))
+                           : "memory");
+            } else if (row_valid) {
+              uint4 o;
+              o.x = pack_bf16x2(g[0], g[1]);
+              o.y = pack_bf16x2(g[2], g[3]);
+              o.z = pack_bf16x2(g[4], g[5]);
+              o.w = pack_bf16x2(g[6], g[7]);
+              *reinterpret_cast<uint4*>(grow_gmem + ck * 8) = o;
+            }
           }
-          fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_gfull(gb));
+          if (MODE == MODE_BWD) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_gfull(gb));
+          }
           ++g_use;
           acc0 += dsum;
           acc1 += bsum;
@@ -510,6 +528,10 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       } else if (MODE == MODE_FWD) {
         const float tot = warp_sum(acc0);
         if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(tot, 0.f);
+      } else if (MODE == MODE_GW) {
+        const float t0s = warp_sum(acc0);
+        const float t1s = warp_sum(acc1);
+        if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(t0s, t1s);
       } else {
         mbar_wait(bar_dafull, item_count & 1);
         tc_fence_after();
