@@ -87,13 +87,15 @@ int make_map(CUtensorMap* map, const void* base, long rows, long cols, long ld, 
 }
 
 // ------------------------------------------------------------------ plans
+constexpr int kSBN = 256;   // S-tile width of the S-only kernels (FWD, GW)
+
 struct FwdPlan {
   int num_rb, num_ct, tiles_per_chunk, total_chunks, m_pad, n_pad, bands;
 };
 FwdPlan fwd_plan(int m_rows, int n_cols) {
   FwdPlan f;
   f.num_rb = ceil_div(m_rows, kBM);
-  f.num_ct = ceil_div(n_cols, kBN);
+  f.num_ct = ceil_div(n_cols, kSBN);
   const long total = (long)f.num_rb * f.num_ct;
   long tpc = total / (148L * 8);
   if (tpc < 1) tpc = 1;
@@ -102,7 +104,7 @@ FwdPlan fwd_plan(int m_rows, int n_cols) {
   f.tiles_per_chunk = (int)tpc;
   f.total_chunks = ceil_div(f.num_ct, f.tiles_per_chunk);
   f.m_pad = f.num_rb * kBM;
-  f.n_pad = f.num_ct * kBN;
+  f.n_pad = f.num_ct * kSBN;
   f.bands = f.m_pad / 32;
   return f;
 }
@@ -214,11 +216,11 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   return w;
 }
 
-template <int MODE, int LOSS, int DC>
+template <int MODE, int LOSS, int DC, int BN>
 int launch_tile(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mbt, const TileParams& p,
                 cudaStream_t st) {
-  using Cfg = TileCfg<MODE, LOSS, DC>;
-  auto kern = tile_kernel<MODE, LOSS, DC>;
+  using Cfg = TileCfg<MODE, LOSS, DC, BN>;
+  auto kern = tile_kernel<MODE, LOSS, DC, BN>;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -248,21 +250,21 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   if (int e = check_shape(sh, ld)) return e;
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
-  const int granule = f.tiles_per_chunk * kBN;
+  const int granule = f.tiles_per_chunk * kSBN;
   if (col_begin < 0 || col_end > sh.n_cols || col_begin >= col_end) return fail(-1, "bad column range [%d,%d)", col_begin, col_end);
   if (col_begin % granule != 0) return fail(-1, "col_begin=%d not a multiple of the granule %d", col_begin, granule);
   if (col_end != sh.n_cols && col_end % granule != 0) return fail(-1, "col_end=%d not a multiple of the granule %d", col_end, granule);
   CUtensorMap ma, mb;
   if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
-  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kBN)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kSBN)) return e;
   TileParams p;
   memset(&p, 0, sizeof p);
   p.m_rows = sh.m_rows;
   p.n_cols = sh.n_cols;
   p.num_kb = ceil_div(ld, kBK);
   p.num_rb = f.num_rb;
-  p.tile_begin = col_begin / kBN;
-  p.tile_end = ceil_div(col_end, kBN);
+  p.tile_begin = col_begin / kSBN;
+  p.tile_end = ceil_div(col_end, kSBN);
   p.tiles_per_chunk = f.tiles_per_chunk;
   p.num_chunks = ceil_div(p.tile_end - p.tile_begin, f.tiles_per_chunk);
   p.chunk_base = p.tile_begin / f.tiles_per_chunk;
@@ -280,8 +282,8 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   p.col_c = reinterpret_cast<float*>(wsb + w.col_c);
   p.diag2 = reinterpret_cast<float*>(wsb + w.diag2);
   p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
-  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWD, LOSS_CLIP, 256>(ma, mb, mb, p, st);
-  return launch_tile<MODE_FWD, LOSS_SIGLIP, 256>(ma, mb, mb, p, st);
+  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWD, LOSS_CLIP, 256, kSBN>(ma, mb, mb, p, st);
+  return launch_tile<MODE_FWD, LOSS_SIGLIP, 256, kSBN>(ma, mb, mb, p, st);
 }
 
 int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt_all, long bt_ld,
@@ -326,11 +328,11 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
   p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part);
   int e = 0;
   if (loss_kind == LOSS_CLIP)
-    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_CLIP, 384>(ma, mb, mbt, p, st)
-                    : launch_tile<MODE_BWD, LOSS_CLIP, 256>(ma, mb, mbt, p, st);
+    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_CLIP, 384, 128>(ma, mb, mbt, p, st)
+                    : launch_tile<MODE_BWD, LOSS_CLIP, 256, 128>(ma, mb, mbt, p, st);
   else
-    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_SIGLIP, 384>(ma, mb, mbt, p, st)
-                    : launch_tile<MODE_BWD, LOSS_SIGLIP, 256>(ma, mb, mbt, p, st);
+    e = b.dc == 384 ? launch_tile<MODE_BWD, LOSS_SIGLIP, 384, 128>(ma, mb, mbt, p, st)
+                    : launch_tile<MODE_BWD, LOSS_SIGLIP, 256, 128>(ma, mb, mbt, p, st);
   if (e) return e;
   {
     const long total = (long)sh.m_rows * (b.d_pad / 4);
@@ -381,7 +383,7 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
   CUtensorMap ma, mb;
   if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
-  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kBN)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kSBN)) return e;
   TileParams p;
   memset(&p, 0, sizeof p);
   p.m_rows = sh.m_rows;
@@ -407,8 +409,8 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
   p.g_out = reinterpret_cast<uint16_t*>(gmat);
   p.g_ld = f.n_pad;
   p.sc_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part);
-  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_GW, LOSS_CLIP, 256>(ma, mb, mb, p, st);
-  return launch_tile<MODE_GW, LOSS_SIGLIP, 256>(ma, mb, mb, p, st);
+  if (loss_kind == LOSS_CLIP) return launch_tile<MODE_GW, LOSS_CLIP, 256, kSBN>(ma, mb, mb, p, st);
+  return launch_tile<MODE_GW, LOSS_SIGLIP, 256, kSBN>(ma, mb, mb, p, st);
 }
 
 // d_out[out_rows, d] = mul * sum_k G(.,.) * Bt[d, k]; transposed=false contracts G's columns (out rows = G rows),
@@ -481,7 +483,7 @@ int mrclip_device_ok(void) {
 }
 
 int mrclip_padded_dim(int d) { return (d + 7) / 8 * 8; }
-int mrclip_padded_cols(int n_cols) { return (n_cols + kBN - 1) / kBN * kBN; }
+int mrclip_padded_cols(int n_cols) { return (n_cols + kSBN - 1) / kSBN * kSBN; }
 
 size_t mrclip_workspace_bytes(int m_rows, int n_cols, int d) {
   if (m_rows <= 0 || n_cols <= 0 || d <= 0) return 0;
@@ -489,8 +491,8 @@ size_t mrclip_workspace_bytes(int m_rows, int n_cols, int d) {
 }
 
 int mrclip_fwd_col_granule(int m_rows, int n_cols) {
-  if (m_rows <= 0 || n_cols <= 0) return kBN;
-  return fwd_plan(m_rows, n_cols).tiles_per_chunk * kBN;
+  if (m_rows <= 0 || n_cols <= 0) return kSBN;
+  return fwd_plan(m_rows, n_cols).tiles_per_chunk * kSBN;
 }
 
 int mrclip_pack_bf16(const void* src, int src_dtype, int rows, int d, long src_ld, void* dst, int dst_ld,

@@ -24,9 +24,8 @@
 namespace mrclip {
 
 constexpr int kBM = 128;           // tile rows  (= TMEM lanes)
-constexpr int kBN = 128;           // tile cols of S
+constexpr int kBN = 128;           // tile cols of S in the fused backward (BN template value there)
 constexpr int kBK = 64;            // K block: 64 bf16 = one 128-byte swizzle row
-constexpr int kStageBytes = 32768; // one pipeline slot: A(16K)+B(16K) or one Bt block (<=32K)
 constexpr int kEpiWarps = 8;
 constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr float kLog2e = 1.4426950408889634f;
@@ -86,30 +85,37 @@ __device__ __forceinline__ float log1p_from_exp(float e) {
   return e <= 0.125f ? series : direct;
 }
 
-template <int MODE, int LOSS, int DC>
+// BN = columns of one S tile: 256 for the S-only modes (FWD, GW: one N=256 MMA per K step, half the
+// A-operand traffic per flop), 128 for the fused backward (TMEM must also hold the dA accumulator).
+template <int MODE, int LOSS, int DC, int BN>
 struct TileCfg {
+  static_assert(BN == 128 || BN == 256, "BN must be 128 or 256");
   static constexpr bool kHasDa = (MODE == MODE_BWD);   // second GEMM fused in the same kernel
+  static_assert(!kHasDa || BN == 128, "fused backward uses 128-wide S tiles");
   static constexpr int kSBufs = (!kHasDa) ? 2 : (DC == 256 ? 2 : 1);
-  static constexpr int kTmemCols = (!kHasDa) ? 256 : 512;
-  static constexpr int kDaCol = kSBufs * kBN;
+  static constexpr int kTmemCols = (!kHasDa) ? 2 * BN : 512;
+  static constexpr int kDaCol = kSBufs * BN;
   static constexpr int kNSub = (DC == 384) ? 2 : 1;
   static constexpr int kDN = DC / kNSub;
-  static constexpr int kStages = (!kHasDa) ? 6 : 5;
+  // one pipeline slot: A(16K)+B(BN*128) for an S step, or one Bt block (<=32K) for a dA step
+  static constexpr int kStageBytes = kHasDa ? 32768 : (kBM * kBK * 2 + BN * kBK * 2);
+  static constexpr int kStages = kHasDa ? 5 : (BN == 256 ? 4 : 6);
   static constexpr int kGBytes = (MODE == MODE_BWD) ? 2 * 32768 : 0;
   static constexpr int kNumBars = 2 * kStages + 10;
   static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kNumBars * 8 + 16 + 1024;
 };
 
-template <int MODE, int LOSS, int DC>
+template <int MODE, int LOSS, int DC, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmBt, const TileParams p) {
-  using Cfg = TileCfg<MODE, LOSS, DC>;
+  using Cfg = TileCfg<MODE, LOSS, DC, BN>;
+  constexpr int kStageBytes = Cfg::kStageBytes;
   constexpr int STAGES = Cfg::kStages;
   constexpr int NSB = Cfg::kSBufs;
   constexpr int DN = Cfg::kDN;
   constexpr int NSUB = Cfg::kNSub;
-  constexpr uint32_t IDESC_S = make_idesc_bf16(kBM, kBN);
+  constexpr uint32_t IDESC_S = make_idesc_bf16(kBM, BN);
   constexpr uint32_t IDESC_D = make_idesc_bf16(kBM, DN);
 
   extern __shared__ uint8_t smem_raw[];
@@ -196,23 +202,23 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(bar_empty(stage), phase ^ 1);
             if (elect_one()) {
-              mbar_expect_tx(bar_full(stage), 2 * kBM * kBK * 2);
+              mbar_expect_tx(bar_full(stage), kBM * kBK * 2 + BN * kBK * 2);
               const uint32_t dst = stage_base + stage * kStageBytes;
               tma_load_2d(dst, &tmA, bar_full(stage), kb * kBK, rb * kBM);
-              tma_load_2d(dst + kBM * kBK * 2, &tmB, bar_full(stage), kb * kBK, t * kBN);
+              tma_load_2d(dst + kBM * kBK * 2, &tmB, bar_full(stage), kb * kBK, t * BN);
             }
             __syncwarp();
             advance();
           }
         };
         auto load_d = [&](int t) {
-          for (int kb2 = 0; kb2 < kBN / kBK; ++kb2) {
+          for (int kb2 = 0; kb2 < BN / kBK; ++kb2) {
             for (int sub = 0; sub < NSUB; ++sub) {
               mbar_wait(bar_empty(stage), phase ^ 1);
               if (elect_one()) {
                 mbar_expect_tx(bar_full(stage), DN * kBK * 2);
                 tma_load_2d(stage_base + stage * kStageBytes, &tmBt, bar_full(stage),
-                            t * kBN + kb2 * kBK, dc * DC + sub * DN);
+                            t * BN + kb2 * kBK, dc * DC + sub * DN);
               }
               __syncwarp();
               advance();
@@ -250,7 +256,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const uint32_t buf = s_use % NSB, use = s_use / NSB;
           mbar_wait(bar_sempty(buf), (use & 1) ^ 1);
           tc_fence_after();
-          const uint32_t d_tmem = tmem_base + buf * kBN;
+          const uint32_t d_tmem = tmem_base + buf * BN;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(bar_full(stage), phase);
             tc_fence_after();
@@ -280,7 +286,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             mbar_wait(bar_daempty, (item_count & 1) ^ 1);
             tc_fence_after();
           }
-          for (int kb2 = 0; kb2 < kBN / kBK; ++kb2) {
+          for (int kb2 = 0; kb2 < BN / kBK; ++kb2) {
             for (int sub = 0; sub < NSUB; ++sub) {
               mbar_wait(bar_full(stage), phase);
               tc_fence_after();
@@ -346,9 +352,11 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t buf = s_use % NSB, use = s_use / NSB;
         mbar_wait(bar_sfull(buf), use & 1);
         tc_fence_after();
+#pragma unroll 1
+        for (int sb = 0; sb < BN / 128; ++sb) {   // this warp's BN/2 columns, 64 at a time
         uint32_t raw[64];
         {
-          const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * kBN + h * 64;
+          const uint32_t taddr = tmem_base + ((q * 32u) << 16) + buf * BN + h * (BN / 2) + sb * 64;
           uint32_t r0[32], r1[32];
           tmem_ld_32x32(taddr, r0);
           tmem_ld_32x32(taddr + 32, r1);
@@ -359,12 +367,13 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             raw[c + 32] = r1[c];
           }
         }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_sempty(buf));
-        ++s_use;
+        if (sb == BN / 128 - 1) {   // accumulator buffer fully drained into registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_sempty(buf));
+        }
 
-        const int col_base = t * kBN + h * 64;
+        const int col_base = t * BN + h * (BN / 2) + sb * 64;
         const bool ragged = (col_base + 64 > p.n_cols);  // warp uniform
         const bool diag_here = (label_w0 + 31 >= col_base) && (label_w0 < col_base + 64);
 
@@ -519,6 +528,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           acc0 += dsum;
           acc1 += bsum;
         }
+        }  // sub-blocks
+        ++s_use;
       }  // tiles
 
       // ------------------------------------------------------------------ item outputs

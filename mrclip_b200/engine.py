@@ -103,6 +103,30 @@ class CudaEngine:
                                                int(accumulate), self._stream()))
 
 
+    # ---- "gmat" backward backend: materialised bf16 gradient block + plain GEMMs ----------------
+    def gmat_bytes(self, m, n):
+        return self.lib.mrclip_gmat_bytes(m, n)
+
+    def clip_gwrite(self, a_rows, b_all, shape, lse2_a, lse2_b, scale, w_own, w_oth, coef, grad_out, ws, gmat,
+                    d_scale, accumulate, both_directions):
+        _cabi.check(self.lib.mrclip_clip_gwrite(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                lse2_a.data_ptr(), lse2_b.data_ptr(), scale.data_ptr(), w_own, w_oth,
+                                                coef, _ptr(grad_out), ws.data_ptr(), gmat.data_ptr(), _ptr(d_scale),
+                                                int(accumulate), int(both_directions), self._stream()))
+
+    def siglip_gwrite(self, a_rows, b_all, shape, scale, bias, coef, grad_out, ws, gmat, d_scale, d_bias, accumulate):
+        _cabi.check(self.lib.mrclip_siglip_gwrite(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                  scale.data_ptr(), _ptr(bias), coef, _ptr(grad_out), ws.data_ptr(),
+                                                  gmat.data_ptr(), _ptr(d_scale), _ptr(d_bias), int(accumulate),
+                                                  self._stream()))
+
+    def gmat_gemm(self, transposed, gmat, shape, bt, ld, coef, scale, grad_out, ws, d_out):
+        """d_out = coef*scale*grad_out * (G . B)  or, transposed, (G^T . A); bt is the transposed operand."""
+        _cabi.check(self.lib.mrclip_gmat_gemm(int(transposed), gmat.data_ptr(), shape, bt.data_ptr(), bt.stride(0), ld,
+                                              coef, scale.data_ptr(), _ptr(grad_out), ws.data_ptr(), d_out.data_ptr(),
+                                              _DT[d_out.dtype], d_out.stride(0), self._stream()))
+
+
 _default_engine = None
 
 

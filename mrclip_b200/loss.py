@@ -25,6 +25,7 @@ There is no CPU path: tensors must live on an sm_100a device, otherwise the call
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -126,6 +127,27 @@ class _Workspace:
         self.diag2 = torch.zeros((n,), dtype=f32, device=device)
         self.in_use = False
         self.transposed = False
+        self.gmat = None
+
+    def gmat_buffer(self, eng):
+        """bf16 scratch for the materialised gradient block G (n x N), allocated on first use."""
+        if self.gmat is None:
+            nbytes = int(eng.gmat_bytes(self.n, self.N))
+            self.gmat = torch.empty(max(nbytes // 2, 8), dtype=torch.bfloat16, device=self.img_all.device)
+        return self.gmat
+
+
+def _use_gmat(eng, ws):
+    """Backward backend: 'gmat' writes G = dLoss/dS once (bf16, n x N) and runs plain GEMMs (4-5 GEMM units
+    per step); 'fused' keeps O(N*D) memory but recomputes S per 384-wide slice of D (7 units).  MRCLIP_BWD
+    = gmat | fused | auto (default: gmat while the block stays under MRCLIP_GMAT_MAX_GIB, 16 GiB)."""
+    mode = os.environ.get("MRCLIP_BWD", "auto").lower()
+    if mode == "fused":
+        return False
+    if mode == "gmat":
+        return True
+    limit = float(os.environ.get("MRCLIP_GMAT_MAX_GIB", "16")) * 2 ** 30
+    return int(eng.gmat_bytes(ws.n, ws.N)) <= limit
 
 
 class _WorkspacePool:
@@ -260,12 +282,24 @@ class _ClipLossFn(torch.autograd.Function):
         d_img = d_txt = d_scale = None
         ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
         # d logit_scale always uses 1/(2n) per rank; global modes average it over ranks below
-        if need_i or need_s:
-            d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+        d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+        d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
+        if _use_gmat(eng, ws):
+            gmat = ws.gmat_buffer(eng)
+            # image rows vs all texts: G block of this rank's rows -> dI_r
+            eng.clip_gwrite(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ctx.scale,
+                            1.0, w_oth, coef, gout, ws.scratch, gmat, ds, True, world == 1)
+            eng.gmat_gemm(False, gmat, shape, ws.txt_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_img)
+            if world == 1:
+                # one rank: the same block, contracted along its rows, is dT
+                eng.gmat_gemm(True, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+            else:
+                eng.clip_gwrite(ws.txt_all[rows], ws.img_all, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
+                                ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, gmat, ds, True, False)
+                eng.gmat_gemm(False, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+        else:
             eng.clip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ws.lse2_row_all[rows], ws.lse2_col_all,
                          ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_img, ds, True)
-        if need_t or need_s:
-            d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
             eng.clip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
                          ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_txt, ds, True)
         if need_s:
@@ -380,13 +414,23 @@ class _SigLipLossFn(torch.autograd.Function):
         d_img = d_txt = d_scale = d_bias = None
         ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
         db = torch.zeros((1,), dtype=torch.float32, device=device) if need_b else None
-        if need_i or need_s or need_b:
-            d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+        d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+        d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
+        # every rank's loss touches T_r: the column block gives the summed (W x) text gradient directly
+        if _use_gmat(eng, ws):
+            gmat = ws.gmat_buffer(eng)
+            eng.siglip_gwrite(ws.img_all[rows], ws.txt_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch, gmat,
+                              ds, db, False)
+            eng.gmat_gemm(False, gmat, shape, ws.txt_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_img)
+            if world == 1:
+                eng.gmat_gemm(True, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+            else:
+                eng.siglip_gwrite(ws.txt_all[rows], ws.img_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
+                                  gmat, None, None, False)
+                eng.gmat_gemm(False, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+        else:
             eng.siglip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
                            d_img, ds, db, False)
-        if need_t:
-            # every rank's loss touches T_r: the column block gives the summed (W x) gradient directly
-            d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
             eng.siglip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
                            d_txt, None, None, False)
         if need_s:

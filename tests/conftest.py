@@ -146,6 +146,62 @@ class StandInEngine:
             val = coef * go * w_own * ((p_own * cos).sum() - cos[idx, idx + shape.label_offset].sum())
             d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + float(val)
 
+    # ---- gmat backend ------------------------------------------------------------------------
+    def gmat_bytes(self, m, n):
+        return m * n * 2
+
+    @staticmethod
+    def _gview(gmat, shape):
+        return gmat[:shape.m_rows * shape.n_cols].view(shape.m_rows, shape.n_cols)
+
+    def clip_gwrite(self, a_rows, b_all, shape, lse2_a, lse2_b, scale, w_own, w_oth, coef, grad_out, ws, gmat,
+                    d_scale, accumulate, both_directions):
+        self.calls.append("clip_gwrite")
+        s = float(scale.item())
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        cos = self._cos(a_rows, b_all)
+        t2 = s * cos * LOG2E
+        p_own = torch.exp2(t2 - lse2_a[:shape.m_rows].double()[:, None])
+        p_oth = torch.exp2(t2 - lse2_b[:shape.n_cols].double()[None, :])
+        g = w_own * p_own + w_oth * p_oth
+        idx = torch.arange(shape.m_rows)
+        g[idx, idx + shape.label_offset] -= (w_own + w_oth)
+        self._gview(gmat, shape).copy_(g.to(torch.bfloat16))
+        if d_scale is not None:
+            dsum = cos[idx, idx + shape.label_offset].sum()
+            val = w_own * ((p_own * cos).sum() - dsum)
+            if both_directions:
+                val = val + w_oth * ((p_oth * cos).sum() - dsum)
+            d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + float(coef * go * val)
+
+    def siglip_gwrite(self, a_rows, b_all, shape, scale, bias, coef, grad_out, ws, gmat, d_scale, d_bias, accumulate):
+        self.calls.append("siglip_gwrite")
+        s = float(scale.item())
+        b = 0.0 if bias is None else float(bias.item())
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        cos = self._cos(a_rows, b_all)
+        g = torch.sigmoid(s * cos + b)
+        idx = torch.arange(shape.m_rows)
+        g[idx, idx + shape.label_offset] -= 1.0
+        self._gview(gmat, shape).copy_(g.to(torch.bfloat16))
+        if d_scale is not None:
+            d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + float(coef * go * (g * cos).sum())
+        if d_bias is not None:
+            d_bias[0] = (float(d_bias[0]) if accumulate else 0.0) + float(coef * go * g.sum())
+
+    def gmat_gemm(self, transposed, gmat, shape, bt, ld, coef, scale, grad_out, ws, d_out):
+        self.calls.append("gmat_gemm")
+        s = float(scale.item())
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        g = self._gview(gmat, shape).double()
+        if transposed:
+            other = bt[:, :shape.m_rows].double().t()      # A  [m, ld]
+            out = g.t() @ other
+        else:
+            other = bt[:, :shape.n_cols].double().t()      # B  [N, ld]
+            out = g @ other
+        d_out.copy_((coef * s * go * out)[:, :d_out.shape[1]].to(d_out.dtype))
+
     def siglip_fwd(self, a_rows, b_all, shape, scale, bias, ws, loss):
         self.calls.append("siglip_fwd")
         s = float(scale.item())

@@ -29,7 +29,7 @@ def test_geometry_entry_points_need_no_gpu():
     lib = _cabi.load()
     assert lib.mrclip_version() >= 100
     assert [lib.mrclip_padded_dim(d) for d in (1, 8, 9, 512, 768)] == [8, 8, 16, 512, 768]
-    assert [lib.mrclip_padded_cols(n) for n in (1, 128, 129, 32768)] == [128, 128, 256, 32768]
+    assert [lib.mrclip_padded_cols(n) for n in (1, 128, 129, 32768)] == [256, 256, 256, 32768]
     assert lib.mrclip_workspace_bytes(0, 10, 10) == 0
     small = lib.mrclip_workspace_bytes(256, 256, 512)
     big = lib.mrclip_workspace_bytes(4096, 32768, 768)

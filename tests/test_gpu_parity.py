@@ -70,8 +70,11 @@ class EmulatedRanks:
     def rows(self, r):
         return slice(r * self.n, (r + 1) * self.n)
 
-    def clip(self, scale, local_loss, gather_with_grad, grad_output=1.0):
+    def clip(self, scale, local_loss, gather_with_grad, grad_output=1.0, backend="fused"):
         eng, dev, W, n, N = self.eng, self.dev, self.W, self.n, self.N
+        gmat = None
+        if backend == "gmat":
+            gmat = torch.empty(int(eng.gmat_bytes(n, N)) // 2, dtype=torch.bfloat16, device=dev)
         s = torch.tensor([scale], dtype=torch.float32, device=dev)
         go = torch.tensor([grad_output], dtype=torch.float32, device=dev)
         stats = torch.zeros((W, 3, N), dtype=torch.float32, device=dev)
@@ -95,10 +98,22 @@ class EmulatedRanks:
             d_i = torch.empty((n, self.d), dtype=torch.float32, device=dev)
             d_t = torch.empty((n, self.d), dtype=torch.float32, device=dev)
             ds = ds_all[r:r + 1]
-            eng.clip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r), lse_row[self.rows(r)],
-                         lse_col, s, 1.0, w_oth, coef, go, self.ws, d_i, ds, True)
-            eng.clip_bwd(self.txt_all[self.rows(r)], self.img_all, self.img_t, self.shape(r), lse_col[self.rows(r)],
-                         lse_row, s, 1.0, w_oth, coef, go, self.ws, d_t, ds, True)
+            ld = self.img_all.shape[1]
+            if backend == "gmat":
+                eng.clip_gwrite(self.img_all[self.rows(r)], self.txt_all, self.shape(r), lse_row[self.rows(r)], lse_col,
+                                s, 1.0, w_oth, coef, go, self.ws, gmat, ds, True, W == 1)
+                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_t, ld, coef, s, go, self.ws, d_i)
+                if W == 1:
+                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_t, ld, coef, s, go, self.ws, d_t)
+                else:
+                    eng.clip_gwrite(self.txt_all[self.rows(r)], self.img_all, self.shape(r), lse_col[self.rows(r)],
+                                    lse_row, s, 1.0, w_oth, coef, go, self.ws, gmat, ds, True, False)
+                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_t, ld, coef, s, go, self.ws, d_t)
+            else:
+                eng.clip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r),
+                             lse_row[self.rows(r)], lse_col, s, 1.0, w_oth, coef, go, self.ws, d_i, ds, True)
+                eng.clip_bwd(self.txt_all[self.rows(r)], self.img_all, self.img_t, self.shape(r),
+                             lse_col[self.rows(r)], lse_row, s, 1.0, w_oth, coef, go, self.ws, d_t, ds, True)
             out.append(dict(d_image=d_i.cpu().numpy(), d_text=d_t.cpu().numpy()))
         ds_all = ds_all * ((0.5 / n) / coef)
         for r in range(W):
@@ -106,8 +121,11 @@ class EmulatedRanks:
             out[r]["d_scale"] = float(ds_all.mean() if global_mode else ds_all[r])
         return out
 
-    def siglip(self, scale, bias, grad_output=1.0):
+    def siglip(self, scale, bias, grad_output=1.0, backend="fused"):
         eng, dev, W, n, N = self.eng, self.dev, self.W, self.n, self.N
+        gmat = None
+        if backend == "gmat":
+            gmat = torch.empty(int(eng.gmat_bytes(n, N)) // 2, dtype=torch.bfloat16, device=dev)
         s = torch.tensor([scale], dtype=torch.float32, device=dev)
         b = torch.tensor([bias], dtype=torch.float32, device=dev)
         go = torch.tensor([grad_output], dtype=torch.float32, device=dev)
@@ -119,10 +137,22 @@ class EmulatedRanks:
             d_i = torch.empty((n, self.d), dtype=torch.float32, device=dev)
             d_t = torch.empty((n, self.d), dtype=torch.float32, device=dev)
             eng.siglip_fwd(self.img_all[self.rows(r)], self.txt_all, self.shape(r), s, b, self.ws, loss)
-            eng.siglip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r), s, b, 1.0 / n, go,
-                           self.ws, d_i, ds, db, False)
-            eng.siglip_bwd(self.txt_all[self.rows(r)], self.img_all, self.img_t, self.shape(r), s, b, 1.0 / n, go,
-                           self.ws, d_t, None, None, False)
+            ld = self.img_all.shape[1]
+            if backend == "gmat":
+                eng.siglip_gwrite(self.img_all[self.rows(r)], self.txt_all, self.shape(r), s, b, 1.0 / n, go, self.ws,
+                                  gmat, ds, db, False)
+                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_t, ld, 1.0 / n, s, go, self.ws, d_i)
+                if W == 1:
+                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_t, ld, 1.0 / n, s, go, self.ws, d_t)
+                else:
+                    eng.siglip_gwrite(self.txt_all[self.rows(r)], self.img_all, self.shape(r), s, b, 1.0 / n, go,
+                                      self.ws, gmat, None, None, False)
+                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_t, ld, 1.0 / n, s, go, self.ws, d_t)
+            else:
+                eng.siglip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r), s, b, 1.0 / n, go,
+                               self.ws, d_i, ds, db, False)
+                eng.siglip_bwd(self.txt_all[self.rows(r)], self.img_all, self.img_t, self.shape(r), s, b, 1.0 / n, go,
+                               self.ws, d_t, None, None, False)
             out.append(dict(loss=float(loss), d_image=d_i.cpu().numpy(), d_text=d_t.cpu().numpy(),
                             d_scale=float(ds), d_bias=float(db)))
         return out
@@ -137,16 +167,19 @@ def _check_rank(out, ref, kind):
         assert abs(out["d_bias"] - float(ref["d_bias"])) <= GRAD_TOL * abs(float(ref["d_bias"])) + 1e-7
 
 
+@pytest.mark.parametrize("backend", ["gmat", "fused"])
 @pytest.mark.parametrize("name", golden_names())
-def test_kernels_match_reference_golden(name):
-    """Every fixture recorded from the reference, all ranks emulated on one GPU through the C ABI."""
+def test_kernels_match_reference_golden(name, backend):
+    """Every fixture recorded from the reference, all ranks emulated on one GPU through the C ABI,
+    for both backward backends (materialised-G GEMMs and the fused recompute row pass)."""
     g = load_golden(name)
     m, W = g["meta"], g["world"]
     em = EmulatedRanks(torch.from_numpy(g["image"]), torch.from_numpy(g["text"]), W)
     if m["kind"] == "clip":
-        out = em.clip(float(m["scale"]), bool(m["local_loss"]), bool(m["gather_with_grad"]), float(m["grad_output"]))
+        out = em.clip(float(m["scale"]), bool(m["local_loss"]), bool(m["gather_with_grad"]), float(m["grad_output"]),
+                      backend=backend)
     else:
-        out = em.siglip(float(m["scale"]), float(m["bias"]), float(m["grad_output"]))
+        out = em.siglip(float(m["scale"]), float(m["bias"]), float(m["grad_output"]), backend=backend)
     for r in range(W):
         _check_rank(out[r], g["ranks"][r], m["kind"])
 
@@ -196,6 +229,7 @@ def test_module_accepts_amp_dtypes(dtype):
     assert rel_err(t.grad.float().cpu().numpy(), ref["d_text"]) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("backend", ["gmat", "fused"])
 @pytest.mark.parametrize("N,D,W,scale,mode", [
     (1024, 768, 1, 14.285714, (False, False)),
     (1536, 512, 4, 100.0, (True, True)),
@@ -203,13 +237,13 @@ def test_module_accepts_amp_dtypes(dtype):
     (130, 40, 2, 14.285714, (True, False)),    # tiny, single partial tile
     (1, 8, 1, 5.0, (False, False)),            # degenerate batch of one
 ])
-def test_clip_vs_oracle(N, D, W, scale, mode):
+def test_clip_vs_oracle(N, D, W, scale, mode, backend):
     from oracle.clip_oracle import clip_loss_oracle
     img, txt = _features(N, D, 1000 + N + D, corr=0.15)
     n = N // W
     parts = lambda x: [x[r * n:(r + 1) * n].numpy() for r in range(W)]
     ref = clip_loss_oracle(parts(img), parts(txt), scale, mode[0], mode[1])
-    out = EmulatedRanks(img, txt, W).clip(scale, mode[0], mode[1])
+    out = EmulatedRanks(img, txt, W).clip(scale, mode[0], mode[1], backend=backend)
     for r in range(W):
         assert abs(out[r]["loss"] - ref[r]["loss"]) <= LOSS_TOL * abs(ref[r]["loss"]) + 1e-6
         assert rel_err(out[r]["d_image"], ref[r]["d_image"]) <= GRAD_TOL
@@ -217,14 +251,15 @@ def test_clip_vs_oracle(N, D, W, scale, mode):
         assert abs(out[r]["d_scale"] - ref[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref[r]["d_logit_scale"]) + 1e-6
 
 
+@pytest.mark.parametrize("backend", ["gmat", "fused"])
 @pytest.mark.parametrize("N,D,W", [(1024, 768, 2), (520, 264, 1), (96, 24, 3)])
-def test_siglip_vs_oracle(N, D, W):
+def test_siglip_vs_oracle(N, D, W, backend):
     from oracle.clip_oracle import siglip_loss_oracle
     img, txt = _features(N, D, 2000 + N)
     n = N // W
     parts = lambda x: [x[r * n:(r + 1) * n].numpy() for r in range(W)]
     ref = siglip_loss_oracle(parts(img), parts(txt), 10.0, -10.0)
-    out = EmulatedRanks(img, txt, W).siglip(10.0, -10.0)
+    out = EmulatedRanks(img, txt, W).siglip(10.0, -10.0, backend=backend)
     for r in range(W):
         assert abs(out[r]["loss"] - ref[r]["loss"]) <= LOSS_TOL * abs(ref[r]["loss"])
         assert rel_err(out[r]["d_image"], ref[r]["d_image"]) <= GRAD_TOL
@@ -251,11 +286,12 @@ def _torch_fp32_clip(img, txt, scale):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("N,D", [(8192, 512), (32768, 768)])
-def test_full_size_vs_torch_fp32_and_properties(N, D):
+@pytest.mark.parametrize("N,D,backend", [(8192, 512, "gmat"), (8192, 512, "fused"), (32768, 768, "gmat")])
+def test_full_size_vs_torch_fp32_and_properties(N, D, backend, monkeypatch):
     """BASELINE sizes (config 3 at world_size 1 is N=32768, D=768): fp32 torch on the same GPU as the
     checker, plus properties that need no checker at all."""
     from mrclip_b200 import ClipLoss
+    monkeypatch.setenv("MRCLIP_BWD", backend)
     dev = torch.device("cuda:0")
     img, txt = _features(N, D, 1234 + 3)
     img, txt = img.to(dev), txt.to(dev)
