@@ -38,6 +38,40 @@ __global__ void pack_bf16_kernel(const void* __restrict__ src, int dtype, int ro
   }
 }
 
+// fast path of the same: d, src_ld, dst_ld multiples of 8 and 16-byte aligned bases; 8 elements per thread
+__global__ void pack_bf16_vec8_kernel(const void* __restrict__ src, int dtype, int rows, int d, long src_ld,
+                                      __nv_bfloat16* __restrict__ dst, int dst_ld) {
+  const int vpr = dst_ld / 8;   // vectors per row
+  const long total = (long)rows * vpr;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / vpr;
+    const int c = (int)(i - r * vpr) * 8;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (c < d) {
+      if (dtype == DT_BF16) {
+        o = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + r * src_ld + c);
+      } else if (dtype == DT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * src_ld + c);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * src_ld + c + 4);
+        o.x = pack_bf16x2(a.x, a.y);
+        o.y = pack_bf16x2(a.z, a.w);
+        o.z = pack_bf16x2(b.x, b.y);
+        o.w = pack_bf16x2(b.z, b.w);
+      } else {
+        const uint4 hv = *reinterpret_cast<const uint4*>(reinterpret_cast<const __half*>(src) + r * src_ld + c);
+        const __half2* h2 = reinterpret_cast<const __half2*>(&hv);
+        const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
+        const float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+        o.x = pack_bf16x2(f0.x, f0.y);
+        o.y = pack_bf16x2(f1.x, f1.y);
+        o.z = pack_bf16x2(f2.x, f2.y);
+        o.w = pack_bf16x2(f3.x, f3.y);
+      }
+    }
+    *reinterpret_cast<uint4*>(dst + r * dst_ld + c) = o;
+  }
+}
+
 // src bf16 [rows, src_ld] (cols valid) -> dst bf16 [cols, dst_ld]
 __global__ void transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int rows, int cols,
                                       long src_ld, __nv_bfloat16* __restrict__ dst, long dst_ld) {
@@ -80,20 +114,30 @@ __global__ void reduce_rows_kernel(const float2* __restrict__ row_part, int slot
   lse2_row[i] = m + log2f(fmaxf(l, 1e-37f));
 }
 
-// per-column merge over the 32-row bands -> (max2, sum) of this rank's rows
+// per-column merge over the 32-row bands -> (max2, sum) of this rank's rows.
+// block = 32 columns x 32 band slices (1024 threads); slices are merged through shared memory.
 __global__ void reduce_cols_kernel(const float* __restrict__ col_l, const float* __restrict__ col_c,
                                    int bands, int n_cols, int n_pad, float* __restrict__ out_m,
                                    float* __restrict__ out_l) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n_cols) return;
+  __shared__ float sm[32][33], sl[32][33];
+  const int c = threadIdx.x, slice = threadIdx.y;
+  const int j = blockIdx.x * 32 + c;
   float m = -CUDART_INF_F, l = 0.f;
-  for (int b = 0; b < bands; ++b) {
-    const float c = col_c[(size_t)b * (n_pad / 64) + j / 64];
-    const float v = col_l[(size_t)b * n_pad + j];
-    lse2_merge(m, l, c, v);
+  if (j < n_cols) {
+    for (int b = slice; b < bands; b += 32) {
+      const float ref = col_c[(size_t)b * (n_pad / 64) + j / 64];
+      const float v = col_l[(size_t)b * n_pad + j];
+      lse2_merge(m, l, ref, v);
+    }
   }
-  out_m[j] = m;
-  out_l[j] = l;
+  sm[slice][c] = m;
+  sl[slice][c] = l;
+  __syncthreads();
+  if (slice == 0 && j < n_cols) {
+    for (int k = 1; k < 32; ++k) lse2_merge(m, l, sm[k][c], sl[k][c]);
+    out_m[j] = m;
+    out_l[j] = l;
+  }
 }
 
 // merge W per-rank (max2,sum) column partials -> lse2 [n_pad], padded with +inf

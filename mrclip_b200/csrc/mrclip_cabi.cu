@@ -500,11 +500,17 @@ int mrclip_pack_bf16(const void* src, int src_dtype, int rows, int d, long src_l
   if (rows <= 0 || d <= 0) return fail(-1, "empty pack");
   if (src_dtype < 0 || src_dtype > 2) return fail(-1, "bad dtype %d", src_dtype);
   if (dst_ld < d) return fail(-1, "dst_ld < d");
-  const long total = (long)rows * dst_ld;
+  const bool vec = d % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+  const long total = vec ? (long)rows * (dst_ld / 8) : (long)rows * dst_ld;
   long blocks = (total + 255) / 256;
-  if (blocks > 148L * 16) blocks = 148L * 16;
-  pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, rows, d, src_ld,
-                                                                  (__nv_bfloat16*)dst, dst_ld);
+  if (blocks > 148L * 32) blocks = 148L * 32;
+  if (vec)
+    pack_bf16_vec8_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, rows, d, src_ld,
+                                                                         (__nv_bfloat16*)dst, dst_ld);
+  else
+    pack_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(src, src_dtype, rows, d, src_ld,
+                                                                    (__nv_bfloat16*)dst, dst_ld);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -536,7 +542,7 @@ int mrclip_clip_fwd_reduce(mrclip_shape sh, void* ws, float* lse2_row, float* co
   uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
   reduce_rows_kernel<<<ceil_div(sh.m_rows, 256), 256, 0, st>>>(
       reinterpret_cast<const float2*>(wsb + w.row_part), f.total_chunks * 2, sh.m_rows, f.m_pad, lse2_row);
-  reduce_cols_kernel<<<ceil_div(sh.n_cols, 256), 256, 0, st>>>(
+  reduce_cols_kernel<<<ceil_div(sh.n_cols, 32), dim3(32, 32), 0, st>>>(
       reinterpret_cast<const float*>(wsb + w.col_l), reinterpret_cast<const float*>(wsb + w.col_c),
       ceil_div(sh.m_rows, 32), sh.n_cols, f.n_pad, col_m, col_l);
   g_launches.fetch_add(2);

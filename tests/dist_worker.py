@@ -1,0 +1,72 @@
+"""torchrun worker for the multi-GPU parity test: every rank runs the public modules on its share of a
+golden case (NCCL), compares with what the reference produced on that rank and exits non-zero on mismatch.
+
+    torchrun --nproc-per-node W tests/dist_worker.py <golden-name> [<golden-name> ...]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from conftest import load_golden, rel_err  # noqa: E402
+from mrclip_b200 import ClipLoss, SigLipLoss  # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"])
+    world = int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    failures = []
+    for name in sys.argv[1:]:
+        case = load_golden(name)
+        m = case["meta"]
+        assert case["world"] == world, (name, case["world"], world)
+        for backend in ("gmat", "fused"):
+            os.environ["MRCLIP_BWD"] = backend
+            n = case["image"].shape[0] // world
+            rows = slice(rank * n, (rank + 1) * n)
+            i = torch.from_numpy(case["image"][rows]).to(dev).requires_grad_(True)
+            t = torch.from_numpy(case["text"][rows]).to(dev).requires_grad_(True)
+            s = torch.tensor(float(m["scale"]), device=dev, requires_grad=True)
+            ref = case["ranks"][rank]
+            if m["kind"] == "clip":
+                mod = ClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
+                               cache_labels=True, rank=rank, world_size=world)
+                loss = mod(i, t, s)
+                nl = n if (world > 1 and m["local_loss"]) else case["image"].shape[0]
+                ok_labels = np.array_equal(mod.get_ground_truth(dev, nl).cpu().numpy(), ref["labels"])
+            else:
+                b = torch.tensor(float(m["bias"]), device=dev, requires_grad=True)
+                loss = SigLipLoss(rank=rank, world_size=world)(i, t, s, b)
+                ok_labels = True
+            (loss * float(m["grad_output"])).backward()
+            errs = dict(loss=abs(loss.item() - float(ref["loss"])) / abs(float(ref["loss"])),
+                        d_image=rel_err(i.grad.cpu().numpy(), ref["d_image"]),
+                        d_text=rel_err(t.grad.cpu().numpy(), ref["d_text"]),
+                        d_scale=abs(s.grad.item() - float(ref["d_scale"])) / max(abs(float(ref["d_scale"])), 1e-6))
+            if m["kind"] == "siglip":
+                errs["d_bias"] = abs(b.grad.item() - float(ref["d_bias"])) / max(abs(float(ref["d_bias"])), 1e-6)
+            bad = [k for k, v in errs.items() if v > (1e-3 if k == "loss" else 1e-2)] + ([] if ok_labels else ["labels"])
+            if bad:
+                failures.append((name, backend, rank, bad, errs))
+            if rank == 0:
+                print(f"{name:32s} {backend:5s} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    flag = torch.tensor([len(failures)], device=dev)
+    dist.all_reduce(flag)
+    for f in failures:
+        print("MISMATCH", f, flush=True)
+    dist.destroy_process_group()
+    sys.exit(1 if flag.item() else 0)
+
+
+if __name__ == "__main__":
+    main()
