@@ -117,9 +117,10 @@ int mrclip_clip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape
 int mrclip_siglip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
                          const float* bias, float coef, const float* grad_out, void* ws, void* gmat, float* d_scale,
                          float* d_bias, int accumulate_scalars, void* stream);
-/* transposed == 0: d_out[m_rows, d] = coef*scale*grad_out * G . B      (bt = B^T, [ld, bt_ld >= n_cols])
- * transposed != 0: d_out[n_cols, d] = coef*scale*grad_out * G^T . A    (bt = A^T, [ld, bt_ld >= m_rows]) */
-int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* bt, long bt_ld, int ld, float coef,
+/* transposed == 0: d_out[m_rows, d] = coef*scale*grad_out * G . B      (feat = b_all,  [n_cols, ld] row-major)
+ * transposed != 0: d_out[n_cols, d] = coef*scale*grad_out * G^T . A    (feat = a_rows, [m_rows, ld] row-major)
+ * The features are consumed as N-major UMMA operands straight from their packed row-major form. */
+int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
                      const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
                      void* stream);
 

@@ -41,7 +41,7 @@ SIGNATURES = {
     "mrclip_gmat_bytes": (C.c_size_t, [_I, _I]),
     "mrclip_clip_gwrite": (_I, [_P, _P, Shape, _I, _P, _P, _P, _F, _F, _F, _P, _P, _P, _P, _I, _I, _P]),
     "mrclip_siglip_gwrite": (_I, [_P, _P, Shape, _I, _P, _P, _F, _P, _P, _P, _P, _P, _I, _P]),
-    "mrclip_gmat_gemm": (_I, [_I, _P, Shape, _P, _L, _I, _F, _P, _P, _P, _P, _I, _L, _P]),
+    "mrclip_gmat_gemm": (_I, [_I, _P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _L, _P]),
     "mrclip_launch_count": (_L, []),
 }
 

@@ -1,13 +1,15 @@
-// Gradient contraction  dA[m, d] = sum_k G[m, k] * Bt[d, k]  as a persistent warp-specialised
+// Gradient contraction  dA[m, d] = sum_k G[m, k] * F[k, d]  as a persistent warp-specialised
 // tcgen05 GEMM (128 x 256 output tiles, K streamed in 64-wide blocks through a TMA ring).
-// G is the bf16 gradient-of-logits block produced by tile_kernel<MODE_GW>; Bt is the other
-// modality's feature matrix transposed ([D, N], K-major for this product).  Split-K partials go
-// to dpart[ks][m_pad][d_pad] and are summed (and scaled / cast) by grad_reduce_kernel.
+// G is the bf16 gradient-of-logits block produced by tile_kernel<MODE_GW>; F is the other
+// modality's packed feature matrix, row-major [K, D].  As a UMMA B operand (N = d, K = k) that is
+// an "MN-major" tile: TMA boxes of [64 k-rows x 64 d-cols] land as 128-byte swizzled rows and the
+// descriptor says N-major, so no transposed copy of the features is ever made.  Split-K partials
+// go to dpart[ks][m_pad][d_pad] and are summed (and scaled / cast) by grad_reduce_kernel.
 //
 // With A_MN (transposed-A variant) the same G block is contracted along its rows instead:
-//   dB[k_col, d] = sum_m G[m, k_col] * Bt'[d, m]   -- A is then an M-major ("MN-major") UMMA operand
-// read from the very same row-major G through a different TMA box / descriptor; this is what lets
-// world_size 1 reuse one G for both gradients.
+//   dB[k_col, d] = sum_m G[m, k_col] * F'[m, d]   -- A is then an M-major UMMA operand read from
+// the very same row-major G through a different TMA box / descriptor; this is what lets one G
+// block serve both gradients.
 //
 // Replaces the autograd matmul-backward GEMMs of loss.py:117-124.
 #pragma once
@@ -52,7 +54,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const GemmParams p) {
   constexpr int STAGES = kGemmStages;
   // instruction descriptor: bit 15 = A is MN-major
-  constexpr uint32_t IDESC = make_idesc_bf16(kBM, kGemmBN) | (A_MN ? (1u << 15) : 0u);
+  constexpr uint32_t IDESC = make_idesc_bf16(kBM, kGemmBN) | (A_MN ? (1u << 15) : 0u) | (1u << 16);  // B is N-major
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -119,7 +121,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           } else {
             tma_load_2d(dst, &tmA, bar_full(stage), kb * kBK, rb * kBM);
           }
-          tma_load_2d(dst + 16384, &tmB, bar_full(stage), kb * kBK, dt * kGemmBN);
+          // F rows kb*64.. (K), columns dt*256.. (N): four boxes of [64 K-rows x 64 N-cols]
+#pragma unroll
+          for (int c = 0; c < kGemmBN / 64; ++c)
+            tma_load_2d(dst + 16384 + c * 8192, &tmB, bar_full(stage), dt * kGemmBN + c * 64, kb * kBK);
         }
         __syncwarp();
         if (++stage == STAGES) {
@@ -141,13 +146,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(bar_full(stage), phase);
         tc_fence_after();
         const uint32_t a = stage_base + stage * kGemmStageBytes;
-        const uint64_t bdesc = make_kmajor_sw128_desc(a + 16384);
+        const uint64_t bdesc = make_mnmajor_sw128_desc(a + 16384, 8192);
         if (A_MN) {
           const uint64_t adesc = make_mnmajor_sw128_desc(a, 8192);
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)  // 16 K-rows = 2 swizzle atoms = 2048 bytes per step
-              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 2 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 128 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit(bar_empty(stage));
           }
         } else {
@@ -155,7 +160,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (elect_one()) {
 #pragma unroll
             for (int k = 0; k < kBK / 16; ++k)
-              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
+              umma_bf16(d_tmem, adesc + 2 * k, bdesc + 128 * k, IDESC, (kb > kb0 || k > 0) ? 1u : 0u);
             umma_commit(bar_empty(stage));
           }
         }

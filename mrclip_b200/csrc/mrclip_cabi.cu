@@ -413,19 +413,18 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
   return launch_tile<MODE_GW, LOSS_SIGLIP, 256, kSBN>(ma, mb, mb, p, st);
 }
 
-// d_out[out_rows, d] = mul * sum_k G(.,.) * Bt[d, k]; transposed=false contracts G's columns (out rows = G rows),
-// transposed=true contracts G's rows (out rows = G columns; G read as an MN-major operand).
-int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* bt, long bt_ld, int d, int ld,
+// d_out[out_rows, d] = mul * sum_k G(.,.) * F[k, d]; transposed=false contracts G's columns (out rows = G rows),
+// transposed=true contracts G's rows (out rows = G columns; G read as an M-major operand).  F = feat [k_len, ld].
+int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* feat, int d, int ld,
                   float coef, const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype,
                   long out_ld, cudaStream_t st) {
   const int out_rows = transposed ? g_cols : g_rows;
   const int k_len = transposed ? g_rows : g_cols;
   const GemmPlan g = gemm_plan(out_rows, k_len, ld);
   const long g_ld = mrclip_padded_cols(g_cols);
-  if (bt_ld < k_len || bt_ld % 8 != 0) return fail(-1, "bt_ld=%ld must be a multiple of 8 and >= %d", bt_ld, k_len);
   CUtensorMap ma, mb;
   if (int e = make_map(&ma, gmat, g_rows, g_cols, g_ld, transposed ? 64 : kBM)) return e;
-  if (int e = make_map(&mb, bt, ld, k_len, bt_ld, kGemmBN)) return e;
+  if (int e = make_map(&mb, feat, k_len, ld, ld, 64)) return e;
   GemmParams p;
   memset(&p, 0, sizeof p);
   p.m_rows = out_rows;
@@ -631,12 +630,12 @@ int mrclip_siglip_gwrite(const void* a_rows, const void* b_all, mrclip_shape sha
   return run_scalar_reduce(shape, ws, coef, coef, grad_out, d_scale, d_bias, accumulate_scalars, 0, st);
 }
 
-int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* bt, long bt_ld, int ld, float coef,
+int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
                      const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
                      void* stream) {
   if (int e = check_shape(shape, ld)) return e;
   if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
-  return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, bt, bt_ld, shape.d, ld, coef, scale, grad_out,
+  return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out,
                        ws, d_out, out_dtype, out_ld, (cudaStream_t)stream);
 }
 

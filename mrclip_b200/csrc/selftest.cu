@@ -274,19 +274,19 @@ static void check_clip(int N, int D, int W, float s, float corr) {
       const char* at = (const char*)d.Tbf + (size_t)r * n * d.ld * 2;
       MR(mrclip_clip_gwrite(ai, d.Tbf, sh, d.ld, lse2_row_all + r * n, lse2_col_all, d.scale, 1.f, 1.f, (float)coef,
                             d.gout, d.ws, gmat, dscale + r, 0, W == 1 ? 1 : 0, 0));
-      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tt, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws,
+      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tbf, d.ld, (float)coef, d.scale, d.gout, d.ws,
                           dA + (size_t)r * n * D, MRCLIP_DT_F32, D, 0));
       CK(cudaDeviceSynchronize());
       CK(cudaMemcpy(hI.data() + (size_t)r * n * D, dA + (size_t)r * n * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost));
       if (W == 1) {
-        MR(mrclip_gmat_gemm(1, gmat, sh, d.It, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+        MR(mrclip_gmat_gemm(1, gmat, sh, d.Ibf, d.ld, (float)coef, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(hT.data(), dA, (size_t)N * D * 4, cudaMemcpyDeviceToHost));
         report("gmat dT (transposed G)", rel_err(dT, hT), 1e-2);
       } else {
         MR(mrclip_clip_gwrite(at, d.Ibf, sh, d.ld, lse2_col_all + r * n, lse2_row_all, d.scale, 1.f, 1.f, (float)coef,
                               d.gout, d.ws, gmat, dscale + r, 1, 0, 0));
-        MR(mrclip_gmat_gemm(0, gmat, sh, d.It, d.npad, d.ld, (float)coef, d.scale, d.gout, d.ws,
+        MR(mrclip_gmat_gemm(0, gmat, sh, d.Ibf, d.ld, (float)coef, d.scale, d.gout, d.ws,
                             dA + (size_t)r * n * D, MRCLIP_DT_F32, D, 0));
         CK(cudaDeviceSynchronize());
         CK(cudaMemcpy(hT.data() + (size_t)r * n * D, dA + (size_t)r * n * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost));
@@ -443,9 +443,9 @@ static void time_shape(int N, int D, int reps) {
       MR(mrclip_clip_gwrite(d.Ibf, d.Tbf, sh, d.ld, lse2_row, lse2_col, d.scale, 1.f, 1.f, 0.5f / N, d.gout, d.ws, gmat,
                             dscale, 0, 1, 0));
       CK(cudaEventRecord(g1));
-      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tt, d.npad, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+      MR(mrclip_gmat_gemm(0, gmat, sh, d.Tbf, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
       CK(cudaEventRecord(g2));
-      MR(mrclip_gmat_gemm(1, gmat, sh, d.It, d.npad, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+      MR(mrclip_gmat_gemm(1, gmat, sh, d.Ibf, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
       CK(cudaEventRecord(g3));
       CK(cudaEventSynchronize(g3));
       float a, b, c;

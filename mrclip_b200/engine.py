@@ -120,9 +120,9 @@ class CudaEngine:
                                                   gmat.data_ptr(), _ptr(d_scale), _ptr(d_bias), int(accumulate),
                                                   self._stream()))
 
-    def gmat_gemm(self, transposed, gmat, shape, bt, ld, coef, scale, grad_out, ws, d_out):
-        """d_out = coef*scale*grad_out * (G . B)  or, transposed, (G^T . A); bt is the transposed operand."""
-        _cabi.check(self.lib.mrclip_gmat_gemm(int(transposed), gmat.data_ptr(), shape, bt.data_ptr(), bt.stride(0), ld,
+    def gmat_gemm(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out):
+        """d_out = coef*scale*grad_out * (G . B) with feat = B [N, ld], or, transposed, (G^T . A) with feat = A [n, ld]."""
+        _cabi.check(self.lib.mrclip_gmat_gemm(int(transposed), gmat.data_ptr(), shape, feat.data_ptr(), feat.shape[1],
                                               coef, scale.data_ptr(), _ptr(grad_out), ws.data_ptr(), d_out.data_ptr(),
                                               _DT[d_out.dtype], d_out.stride(0), self._stream()))
 

@@ -277,7 +277,6 @@ class _ClipLossFn(torch.autograd.Function):
             coef = 0.5 / n          # 1/(2n): W x the global-mean gradient, or the local loss itself
         w_oth = 0.0 if (world > 1 and module.local_loss and not module.gather_with_grad) else 1.0
 
-        _ensure_transposed(eng, ws)
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_scale = None
         ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
@@ -289,15 +288,16 @@ class _ClipLossFn(torch.autograd.Function):
             # image rows vs all texts: G block of this rank's rows -> dI_r
             eng.clip_gwrite(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ctx.scale,
                             1.0, w_oth, coef, gout, ws.scratch, gmat, ds, True, world == 1)
-            eng.gmat_gemm(False, gmat, shape, ws.txt_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_img)
+            eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
             if world == 1:
                 # one rank: the same block, contracted along its rows, is dT
-                eng.gmat_gemm(True, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
             else:
                 eng.clip_gwrite(ws.txt_all[rows], ws.img_all, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
                                 ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, gmat, ds, True, False)
-                eng.gmat_gemm(False, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+                eng.gmat_gemm(False, gmat, shape, ws.img_all, coef, ctx.scale, gout, ws.scratch, d_txt)
         else:
+            _ensure_transposed(eng, ws)
             eng.clip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ws.lse2_row_all[rows], ws.lse2_col_all,
                          ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_img, ds, True)
             eng.clip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
@@ -408,7 +408,6 @@ class _SigLipLossFn(torch.autograd.Function):
         shape = Shape(n, N, d, rank * n)
         gout = grad_output.detach().reshape(1).to(torch.float32).contiguous()
         coef = 1.0 / n
-        _ensure_transposed(eng, ws)
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         need_b = ctx.needs_input_grad[3] and ctx.bias_meta is not None
         d_img = d_txt = d_scale = d_bias = None
@@ -421,14 +420,15 @@ class _SigLipLossFn(torch.autograd.Function):
             gmat = ws.gmat_buffer(eng)
             eng.siglip_gwrite(ws.img_all[rows], ws.txt_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch, gmat,
                               ds, db, False)
-            eng.gmat_gemm(False, gmat, shape, ws.txt_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_img)
+            eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
             if world == 1:
-                eng.gmat_gemm(True, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
             else:
                 eng.siglip_gwrite(ws.txt_all[rows], ws.img_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
                                   gmat, None, None, False)
-                eng.gmat_gemm(False, gmat, shape, ws.img_t, ws.ld, coef, ctx.scale, gout, ws.scratch, d_txt)
+                eng.gmat_gemm(False, gmat, shape, ws.img_all, coef, ctx.scale, gout, ws.scratch, d_txt)
         else:
+            _ensure_transposed(eng, ws)
             eng.siglip_bwd(ws.img_all[rows], ws.txt_all, ws.txt_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,
                            d_img, ds, db, False)
             eng.siglip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch,

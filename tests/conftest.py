@@ -189,17 +189,13 @@ class StandInEngine:
         if d_bias is not None:
             d_bias[0] = (float(d_bias[0]) if accumulate else 0.0) + float(coef * go * g.sum())
 
-    def gmat_gemm(self, transposed, gmat, shape, bt, ld, coef, scale, grad_out, ws, d_out):
+    def gmat_gemm(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out):
         self.calls.append("gmat_gemm")
         s = float(scale.item())
         go = 1.0 if grad_out is None else float(grad_out.item())
         g = self._gview(gmat, shape).double()
-        if transposed:
-            other = bt[:, :shape.m_rows].double().t()      # A  [m, ld]
-            out = g.t() @ other
-        else:
-            other = bt[:, :shape.n_cols].double().t()      # B  [N, ld]
-            out = g @ other
+        assert feat.shape[0] == (shape.m_rows if transposed else shape.n_cols)
+        out = (g.t() if transposed else g) @ feat.double()
         d_out.copy_((coef * s * go * out)[:, :d_out.shape[1]].to(d_out.dtype))
 
     def siglip_fwd(self, a_rows, b_all, shape, scale, bias, ws, loss):

@@ -102,13 +102,13 @@ class EmulatedRanks:
             if backend == "gmat":
                 eng.clip_gwrite(self.img_all[self.rows(r)], self.txt_all, self.shape(r), lse_row[self.rows(r)], lse_col,
                                 s, 1.0, w_oth, coef, go, self.ws, gmat, ds, True, W == 1)
-                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_t, ld, coef, s, go, self.ws, d_i)
+                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_all, coef, s, go, self.ws, d_i)
                 if W == 1:
-                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_t, ld, coef, s, go, self.ws, d_t)
+                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_all[self.rows(r)], coef, s, go, self.ws, d_t)
                 else:
                     eng.clip_gwrite(self.txt_all[self.rows(r)], self.img_all, self.shape(r), lse_col[self.rows(r)],
                                     lse_row, s, 1.0, w_oth, coef, go, self.ws, gmat, ds, True, False)
-                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_t, ld, coef, s, go, self.ws, d_t)
+                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_all, coef, s, go, self.ws, d_t)
             else:
                 eng.clip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r),
                              lse_row[self.rows(r)], lse_col, s, 1.0, w_oth, coef, go, self.ws, d_i, ds, True)
@@ -141,13 +141,13 @@ class EmulatedRanks:
             if backend == "gmat":
                 eng.siglip_gwrite(self.img_all[self.rows(r)], self.txt_all, self.shape(r), s, b, 1.0 / n, go, self.ws,
                                   gmat, ds, db, False)
-                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_t, ld, 1.0 / n, s, go, self.ws, d_i)
+                eng.gmat_gemm(False, gmat, self.shape(r), self.txt_all, 1.0 / n, s, go, self.ws, d_i)
                 if W == 1:
-                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_t, ld, 1.0 / n, s, go, self.ws, d_t)
+                    eng.gmat_gemm(True, gmat, self.shape(r), self.img_all[self.rows(r)], 1.0 / n, s, go, self.ws, d_t)
                 else:
                     eng.siglip_gwrite(self.txt_all[self.rows(r)], self.img_all, self.shape(r), s, b, 1.0 / n, go,
                                       self.ws, gmat, None, None, False)
-                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_t, ld, 1.0 / n, s, go, self.ws, d_t)
+                    eng.gmat_gemm(False, gmat, self.shape(r), self.img_all, 1.0 / n, s, go, self.ws, d_t)
             else:
                 eng.siglip_bwd(self.img_all[self.rows(r)], self.txt_all, self.txt_t, self.shape(r), s, b, 1.0 / n, go,
                                self.ws, d_i, ds, db, False)
