@@ -102,7 +102,11 @@ struct TileCfg {
   static constexpr int kStages = kHasDa ? 5 : (BN == 256 ? 4 : 6);
   static constexpr int kGBytes = (MODE == MODE_BWD) ? 2 * 32768 : 0;
   static constexpr int kNumBars = 2 * kStages + 10;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kNumBars * 8 + 16 + 1024;
+  // GW: each epilogue warp keeps the other-direction LSE of its BN/2 columns in a private smem strip
+  // (fetched before the accumulator wait, so the global-load latency is off the critical path)
+  static constexpr bool kLseSmem = (MODE == MODE_GW && LOSS == LOSS_CLIP);
+  static constexpr int kLseBytes = kLseSmem ? kEpiWarps * (BN / 2) * 4 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kLseBytes + kNumBars * 8 + 16 + 1024;
 };
 
 template <int MODE, int LOSS, int DC, int BN>
@@ -123,7 +127,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_base = smem_u32(smem);
   const uint32_t g_base = stage_base + STAGES * kStageBytes;
-  uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes;
+  const uint32_t lse_smem = g_base + Cfg::kGBytes;
+  uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes + Cfg::kLseBytes;
   const uint32_t bar_base = smem_u32(bar_ptr);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + Cfg::kNumBars * 8);
 
@@ -350,8 +355,17 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
       for (int t = t0; t < t1; ++t) {
         const uint32_t buf = s_use % NSB, use = s_use / NSB;
+        float4 lbv = make_float4(0.f, 0.f, 0.f, 0.f);
+        const uint32_t lse_w = lse_smem + (warp - 2) * (BN / 2) * 4;
+        if (Cfg::kLseSmem)
+          lbv = __ldg(reinterpret_cast<const float4*>(p.lse2_b + t * BN + h * (BN / 2)) + lane);
         mbar_wait(bar_sfull(buf), use & 1);
         tc_fence_after();
+        if (Cfg::kLseSmem) {
+          __syncwarp();   // every lane is done with the previous tile's strip
+          sts_f4(lse_w + 16 * lane, lbv);
+          __syncwarp();
+        }
 #pragma unroll 1
         for (int sb = 0; sb < BN / 128; ++sb) {   // this warp's BN/2 columns, 64 at a time
         uint32_t raw[64];
@@ -449,10 +463,14 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int ck = 0; ck < 8; ++ck) {
             float g[8];
             if (LOSS == LOSS_CLIP) {
-              const float4 lb0 =
-                  __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8));
-              const float4 lb1 =
-                  __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8 + 4));
+              float4 lb0, lb1;
+              if (Cfg::kLseSmem) {
+                lb0 = lds_f4(lse_w + (sb * 64 + ck * 8) * 4);
+                lb1 = lds_f4(lse_w + (sb * 64 + ck * 8) * 4 + 16);
+              } else {
+                lb0 = __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8));
+                lb1 = __ldg(reinterpret_cast<const float4*>(p.lse2_b + col_base + ck * 8 + 4));
+              }
               const float lb[8] = {lb0.x, lb0.y, lb0.z, lb0.w, lb1.x, lb1.y, lb1.z, lb1.w};
 #pragma unroll
               for (int j = 0; j < 8; ++j) {
