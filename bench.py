@@ -197,10 +197,12 @@ def run_ours(args):
     # per-operation device time, live: CUDA events around every engine call (= kernel launch group) on the
     # launching stream; the roofline is quoted for the costliest op that carries algorithmic flops
     ALG_OPS = {"clip_fwd_tiles": "tile_kernel<MODE_FWD> (S = A.B^T tiles + online LSE, 2nND flop)",
+               "clip_fwd_tiles_e": "tile_kernel<MODE_FWDE> (S = A.B^T tiles + online LSE + bf16 E block out, 2nND flop)",
                "gmat_gemm": "gemm_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, 2nND flop per launch)",
+               "gmat_gemm_dot": "gemm_kernel (dA = G.B from the bf16 gradient block, 2nND flop per launch)",
                "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)"}
-    TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_reduce", "lse2_merge", "clip_loss", "clip_gwrite",
-             "gmat_gemm", "clip_bwd"]
+    TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "clip_fwd_reduce", "lse2_merge", "clip_loss",
+             "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "clip_bwd"]
     ev = {k: [] for k in TIMED}
     originals = {k: getattr(eng, k) for k in TIMED}
 

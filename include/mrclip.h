@@ -124,6 +124,47 @@ int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const
                      const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
                      void* stream);
 
+/* ---- "emat" backend: nothing N x N is ever recomputed ----------------------------------------------- */
+/* The forward of ClipLoss already evaluates E_ij = 2^(S2_ij - c) for its online LSE (c = maximum of the
+ * 32 x 64 sub-tile, S2 = S*log2(e)).  mrclip_clip_fwd_tiles_e is mrclip_clip_fwd_tiles that also stores E as bf16
+ * into emat [m_pad, mrclip_padded_cols(n_cols)] (mrclip_gmat_bytes) through TMA; the references c stay in ws.
+ * The backward then needs no S tiles: mrclip_emat_transform rewrites the block in place (one HBM pass),
+ *   G_ij = E_ij * (w_row*2^(c - lse2_row_i) + w_col*2^(c - lse2_col_j)),   positives exactly (fp32, from diag2),
+ * and both gradients are plain mrclip_gmat_gemm calls: 3 N x N x D contractions per step instead of 4-5.
+ * Replaces loss.py:117-124 + :135-136 and their autograd graph like the other backends. */
+int mrclip_clip_fwd_tiles_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                            int col_begin, int col_end, void* ws, void* emat, void* stream);
+/* Guard: bf16 E flushes to zero 126 binary orders below its sub-tile reference.  Raises the device flag
+ * mrclip_emat_flag(shape, ws) when some row/column LSE lies more than 80 binary orders below a reference, i.e.
+ * when a flushed entry could carry gradient.  mrclip_clip_gwrite_if (exact recompute of G into the same block)
+ * runs only while the flag is set (run_if), mrclip_emat_transform only while it is clear (skip_if). */
+int mrclip_emat_check(mrclip_shape shape, void* ws, const float* lse2_row, const float* lse2_col, void* stream);
+const int* mrclip_emat_flag(mrclip_shape shape, void* ws);
+int mrclip_clip_gwrite_if(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* lse2_a,
+                          const float* lse2_b, const float* scale, float w_own, float w_oth, void* ws, void* gmat,
+                          const int* run_if, void* stream);
+/* lse2_row indexes emat rows, lse2_col (padded, +inf) its columns, diag2 its rows.
+ * msums (optional, float [2][ranks], zeroed here): what d(loss)/d(logit_scale) needs, split by the rank that
+ * owns the column (n_per_rank columns each):
+ *   msums[0][r] = sum_{i, j in rank r} w_row * Prow_ij * log2 Prow_ij,   msums[1][r] = same with w_col * Pcol,
+ * log2 P recovered as c + log2(E) - lse2 (positives exact).  With L_q the local loss (natural log) of rank q,
+ *   scale * dL_q/dscale = L_q + ln2/(2n) * (sum_r msums_q[0][r] + sum_p msums_p[1][q]);
+ * with the guard raised the same sums are taken from the exact recompute's partials (chunk granularity). */
+int mrclip_emat_transform(mrclip_shape shape, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
+                          const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
+                          float* msums, int n_per_rank, int ranks, void* stream);
+/* mrclip_gmat_gemm with  dot_out += <d_out, dot_feat> / scale  (dot_feat: bf16 [out_rows, ld]): with d_out = dA and
+ * dot_feat = A this is d(loss)/d(scale), by homogeneity of S = scale * A.B^T. */
+int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                         const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
+                         const void* dot_feat, float* dot_out, void* stream);
+/* SigLipLoss has no normaliser: its forward can store G = sigmoid(z) - [j==label_i] directly (then both
+ * gradients are plain mrclip_gmat_gemm calls) and leaves the d_scale / d_bias partial sums in ws. */
+int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                        const float* bias, void* ws, float* loss, void* gmat, void* stream);
+int mrclip_siglip_e_scalars(mrclip_shape shape, void* ws, float coef, const float* grad_out, float* d_scale,
+                            float* d_bias, int accumulate_scalars, void* stream);
+
 /* number of kernels this library has launched on behalf of the calling process (for bench accounting) */
 long mrclip_launch_count(void);
 

@@ -216,11 +216,13 @@ __global__ void scalar_reduce_kernel(const float2* __restrict__ part, long count
 __global__ void grad_reduce_kernel(const float* __restrict__ dpart, int cs, int m_rows, int d,
                                    int m_pad, int d_pad, float coef, const float* __restrict__ scale,
                                    const float* __restrict__ grad_out, void* __restrict__ out,
-                                   int out_dtype, long out_ld) {
+                                   int out_dtype, long out_ld, const __nv_bfloat16* __restrict__ dot_feat,
+                                   long dot_ld, float* __restrict__ dot_out) {
   float mul = coef * scale[0];
   if (grad_out) mul *= grad_out[0];
   const int dq = d_pad / 4;
   const long total = (long)m_rows * dq;
+  float dot = 0.f;   // <out, dot_feat>: with out = dA this is  scale * dLoss/dscale  (homogeneity of S = scale*A.B^T)
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total;
        i += (long)gridDim.x * blockDim.x) {
     const long r = i / dq;
@@ -237,8 +239,247 @@ __global__ void grad_reduce_kernel(const float* __restrict__ dpart, int cs, int 
     const float o[4] = {a.x * mul, a.y * mul, a.z * mul, a.w * mul};
 #pragma unroll
     for (int j = 0; j < 4; ++j)
-      if (c + j < d) store_from_float(out, out_dtype, (size_t)(r * out_ld + c + j), o[j]);
+      if (c + j < d) {
+        store_from_float(out, out_dtype, (size_t)(r * out_ld + c + j), o[j]);
+        if (dot_feat) dot = fmaf(o[j], __bfloat162float(dot_feat[r * dot_ld + c + j]), dot);
+      }
   }
+  if (dot_feat) {
+    __shared__ float red[32];
+    dot = warp_sum(dot);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = dot;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float t = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+      t = warp_sum(t);
+      if (threadIdx.x == 0) atomicAdd(dot_out, t / scale[0]);
+    }
+  }
+}
+
+// ---- E-block guard -------------------------------------------------------------------------------
+// The backward rebuilds G_ij = E_ij * (2^(c-lr_i) + 2^(c-lc_j)) from the bf16 E block, c = sub-tile reference.
+// An entry whose E flushed to zero (S2_ij < c - 126) still matters only if S2_ij is within ~2^-40 of its row or
+// column LSE, which needs  lr_i < c - 80  or  lc_j < c - 80  somewhere in the sub-tile.  cbmin = per 64-column
+// block minimum of lse2_col; the flag is raised when any sub-tile violates the bound (then the exact recompute
+// kernel rewrites the block with G and the GEMMs skip their transform).
+__global__ void emat_cbmin_kernel(const float* __restrict__ lse2_col, int ncb, float* __restrict__ cbmin,
+                                  int* __restrict__ flag) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *flag = 0;
+  if (w >= ncb) return;
+  const float2 v = reinterpret_cast<const float2*>(lse2_col + (size_t)w * 64)[lane];
+  float m = fminf(v.x, v.y);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) cbmin[w] = m;
+}
+__global__ void emat_check_kernel(const float* __restrict__ colc, const float* __restrict__ lse2_row, int m_rows,
+                                  const float* __restrict__ cbmin, int ncb, float limit, int* __restrict__ flag) {
+  __shared__ float s_lrmin;
+  const int band = blockIdx.x;
+  if (threadIdx.x < 32) {
+    const int i = band * 32 + threadIdx.x;
+    float m = (i < m_rows) ? lse2_row[i] : CUDART_INF_F;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) s_lrmin = m;
+  }
+  __syncthreads();
+  const float lrmin = s_lrmin;
+  bool bad = false;
+  for (int cb = threadIdx.x; cb < ncb; cb += blockDim.x) {
+    const float c = colc[(size_t)band * ncb + cb];
+    bad |= (c - lrmin > limit) || (c - cbmin[cb] > limit);
+  }
+  if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(flag, 1);
+}
+
+// E block -> G block, in place (HBM-bound: one read and one write of the bf16 [m_pad, n_pad] block).
+//   G_ij = E_ij * (w_row * 2^(c - lse2_row_i) + w_col * 2^(c - lse2_col_j)),  c = colc[i/32][j/64]
+//   G_i,label(i) = w_row * 2^(diag2_i - lse2_row_i) + w_col * 2^(diag2_i - lse2_col_label) - (w_row + w_col)   (exact)
+// One block = one 32-row band x 1024 columns: the 1024 column factors are built once in shared memory and
+// reused by the 32 rows; a thread owns 8 consecutive columns (16 bytes) of a row.  Skipped when *skip_if != 0
+// (the exact recompute fallback has already written G).
+//
+// WSUM: the pass also accumulates what d(loss)/d(logit_scale) needs, split by the rank that owns the column
+// (n_per_rank columns each).  With L_q the local loss of rank q (natural log) and P the two softmaxes,
+//   scale * dL_q/dscale = L_q + ln2/(2n) * ( sum_{i in q, all j} Prow_ij log2 Prow_ij + sum_{all i, j in q} Pcol_ij log2 Pcol_ij )
+// (the sum_j P = 1 identities absorb the lse and delta terms into L_q), so only the negative entropies are needed:
+//   msums[0][r] += sum_{i, j in rank r} w_row * Prow_ij * log2 Prow_ij,     msums[1][r] += same with w_col * Pcol,
+// log2 P = c + log2(E) - lse2 recovered from the stored exponential (positives: exact, from diag2).  The error
+// of a bf16-rounded E then scales with the entropy, not with |S2|, and nothing cancels against an exact term.
+template <bool WSUM>
+__global__ void __launch_bounds__(256)
+emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pad, const float* __restrict__ colc,
+                      int ncb, const float* __restrict__ lse2_row, const float* __restrict__ lse2_col,
+                      const float* __restrict__ diag2, int label_offset, float w_row, float w_col,
+                      const int* __restrict__ skip_if, float* __restrict__ msums, int n_per_rank, int ranks) {
+  if (skip_if != nullptr && __ldg(skip_if) != 0) return;
+  __shared__ __align__(16) float cfac[1024];
+  __shared__ __align__(16) float lcol[WSUM ? 1024 : 4];
+  __shared__ float bacc[4][2];
+  const int band = blockIdx.y;
+  const int col0 = blockIdx.x * 1024;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* cw_row = colc + (size_t)band * ncb;
+  for (int c = tid; c < 1024; c += 256) {
+    const int j = col0 + c;
+    float f = 0.f, lc = CUDART_INF_F;
+    if (j < n_pad) {
+      lc = __ldg(lse2_col + j);
+      f = w_col * ex2f(fminf(__ldg(cw_row + (j >> 6)) - lc, 120.f));
+    }
+    cfac[c] = f;
+    if (WSUM) lcol[c] = lc;
+  }
+  if (WSUM && tid < 8) bacc[tid >> 1][tid & 1] = 0.f;
+  __syncthreads();
+  const float wsum = w_row + w_col;
+  float accr[4] = {0.f, 0.f, 0.f, 0.f}, accc[4] = {0.f, 0.f, 0.f, 0.f};
+  bool strad[4] = {false, false, false, false};   // this thread's 8 columns of segment s straddle two ranks
+  if (WSUM && n_per_rank % 8 != 0) {
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg) {
+      const int j = col0 + seg * 256 + lane * 8;
+      strad[seg] = (j / n_per_rank) != ((j + 7) / n_per_rank);
+    }
+  }
+#pragma unroll 1
+  for (int rr = warp; rr < 32; rr += 8) {
+    const int i = band * 32 + rr;
+    const float lr = (i < m_rows) ? __ldg(lse2_row + i) : CUDART_INF_F;
+    const int jd = i + label_offset;   // column of this row's positive
+    uint16_t* row = emat + (size_t)i * ld;
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg) {
+      const int c = seg * 256 + lane * 8;
+      const int j = col0 + c;
+      if (j >= n_pad) continue;
+      uint4 v = *reinterpret_cast<const uint4*>(row + j);
+      const float cw = __ldg(cw_row + (j >> 6));
+      const float rf = w_row * ex2f(fminf(cw - lr, 120.f));
+      const float4 f0 = *reinterpret_cast<const float4*>(cfac + c);
+      const float4 f1 = *reinterpret_cast<const float4*>(cfac + c + 4);
+      const float cf[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+      uint32_t w[4] = {v.x, v.y, v.z, v.w};
+      float e[8], g[8];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        e[2 * k] = __uint_as_float(w[k] << 16);
+        e[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = e[k] * (rf + cf[k]);
+      const bool diag_here = (jd >= j && jd < j + 8 && i < m_rows);
+      float dg = 0.f;
+      if (diag_here) {
+        dg = __ldg(diag2 + i);
+        const float gd = w_row * ex2f(dg - lr) + w_col * ex2f(dg - __ldg(lse2_col + jd)) - wsum;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k == jd - j) g[k] = gd;
+      }
+      if (WSUM) {
+        const float4 l0 = *reinterpret_cast<const float4*>(lcol + c);
+        const float4 l1 = *reinterpret_cast<const float4*>(lcol + c + 4);
+        const float lc[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        float tr[8], tc[8];   // w * P * log2 P per element, both directions (0 for flushed / padded entries)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float s2 = cw + lg2f(e[k]);
+          const bool live = e[k] > 0.f;
+          tr[k] = live ? e[k] * rf * (s2 - lr) : 0.f;
+          tc[k] = live ? e[k] * cf[k] * (s2 - lc[k]) : 0.f;
+        }
+        if (diag_here) {   // the positive: exact probabilities from diag2
+          const float lpr = dg - lr, lpc = dg - __ldg(lse2_col + jd);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (k == jd - j) {
+              tr[k] = w_row * ex2f(lpr) * lpr;
+              tc[k] = w_col * ex2f(lpc) * lpc;
+            }
+        }
+        if (!strad[seg]) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            accr[seg] += tr[k];
+            accc[seg] += tc[k];
+          }
+        } else {   // the 8 columns straddle two ranks (n not a multiple of 8): attribute element-wise, rarely taken
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            if (j + k < n_per_rank * ranks) {
+              const int r = (j + k) / n_per_rank;
+              atomicAdd(msums + r, tr[k]);
+              atomicAdd(msums + ranks + r, tc[k]);
+            }
+          }
+        }
+      }
+      v.x = pack_bf16x2(g[0], g[1]);
+      v.y = pack_bf16x2(g[2], g[3]);
+      v.z = pack_bf16x2(g[4], g[5]);
+      v.w = pack_bf16x2(g[6], g[7]);
+      *reinterpret_cast<uint4*>(row + j) = v;
+    }
+  }
+  if (WSUM) {
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg) {
+      const int j_lo = col0 + seg * 256, j_hi = j_lo + 255;
+      const int n_all = n_per_rank * ranks;
+      if (j_lo >= n_all) continue;
+      const int r_lo = j_lo / n_per_rank, r_hi = min(j_hi, n_all - 1) / n_per_rank;
+      if (r_lo == r_hi) {   // the whole 256-column segment belongs to one rank (block-uniform)
+        const float tr = warp_sum(accr[seg]), tc = warp_sum(accc[seg]);
+        if (lane == 0) {
+          atomicAdd(&bacc[seg][0], tr);
+          atomicAdd(&bacc[seg][1], tc);
+        }
+      } else {
+        const int j = j_lo + lane * 8;
+        if (j < n_all) {
+          const int r = min(j / n_per_rank, ranks - 1);
+          atomicAdd(msums + r, accr[seg]);
+          atomicAdd(msums + ranks + r, accc[seg]);
+        }
+      }
+    }
+    __syncthreads();
+    if (tid < 8) {
+      const int seg = tid >> 1, which = tid & 1;
+      const int j_lo = col0 + seg * 256, n_all = n_per_rank * ranks;
+      if (j_lo < n_all) {
+        const int r_lo = j_lo / n_per_rank, r_hi = min(j_lo + 255, n_all - 1) / n_per_rank;
+        if (r_lo == r_hi) atomicAdd(msums + which * ranks + r_lo, bacc[seg][which]);
+      }
+    }
+  }
+}
+
+// Fallback twin of the WSUM accumulation: when the guard flag is set, G was written by tile_kernel<MODE_GW>
+// run with TileParams::ent, whose per-item scalar partials (x = sum Prow log2 Prow, y = sum Pcol log2 Pcol over
+// one row block x one column chunk) are attributed to the rank owning the chunk's first column.
+__global__ void emat_fallback_sums_kernel(const int* __restrict__ run_if, const float2* __restrict__ sc_part,
+                                          int num_rb, int num_chunks, int chunk_cols, int n_per_rank, int ranks,
+                                          const float* __restrict__ scale, float* __restrict__ msums) {
+  if (__ldg(run_if) == 0) return;
+  (void)scale;
+  const float to_log2 = 1.f;
+  const int item = blockIdx.x * blockDim.x + threadIdx.x;
+  if (item >= num_rb * num_chunks) return;
+  const int chunk = item / num_rb;
+  const int r = min((chunk * chunk_cols) / n_per_rank, ranks - 1);
+  float x = 0.f, y = 0.f;
+  for (int w = 0; w < 8; ++w) {
+    const float2 v = sc_part[(size_t)item * 8 + w];
+    x += v.x;
+    y += v.y;
+  }
+  atomicAdd(msums + r, x * to_log2);
+  atomicAdd(msums + ranks + r, y * to_log2);
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long n, float v) {

@@ -70,6 +70,7 @@ EncodeTiledFn encode_fn() {
 
 // bf16 matrix [rows, cols] with row stride ld elements; box = [box_rows, 64 cols], 128B swizzle
 int make_map(CUtensorMap* map, const void* base, long rows, long cols, long ld, int box_rows) {
+  // (also used for the E store map: box [32 rows x 64 cols])
   // box is always 64 elements (128 bytes) wide: one swizzle row
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(-2, "cuTensorMapEncodeTiled entry point not available");
@@ -178,7 +179,7 @@ GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
 }
 
 struct WsLayout {
-  size_t row_part, col_l, col_c, diag2, sc_part, dpart, total;
+  size_t row_part, col_l, col_c, diag2, sc_part, sc_part2, cbmin, flag, dpart, total;
 };
 WsLayout ws_layout(int m_rows, int n_cols, int d) {
   const int ld = mrclip_padded_dim(d);
@@ -191,8 +192,6 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   off += align_up((size_t)f.total_chunks * 2 * f.m_pad * sizeof(float2), 256);
   w.col_l = off;
   off += align_up((size_t)f.bands * f.n_pad * sizeof(float), 256);
-  w.col_c = off;
-  off += align_up((size_t)f.bands * (f.n_pad / 64) * sizeof(float), 256);
   w.diag2 = off;
   off += align_up((size_t)f.m_pad * sizeof(float), 256);
   const size_t fwd_end = off;
@@ -212,6 +211,16 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   const size_t items_f = (size_t)f.num_rb * f.total_chunks;
   const size_t items = items_f > (size_t)b.num_items ? items_f : (size_t)b.num_items;
   off += align_up(items * kEpiWarps * sizeof(float2), 256);
+  // regions that must survive from the forward into the backward (never aliased by dpart):
+  // the sub-tile references of E, SigLIP's d_scale/d_bias partials, the E-block guard
+  w.col_c = off;
+  off += align_up((size_t)f.bands * (f.n_pad / 64) * sizeof(float), 256);
+  w.sc_part2 = off;
+  off += align_up(items_f * kEpiWarps * sizeof(float2), 256);
+  w.cbmin = off;
+  off += align_up((size_t)(f.n_pad / 64) * sizeof(float), 256);
+  w.flag = off;
+  off += 256;
   w.total = off;
   return w;
 }
@@ -246,7 +255,8 @@ int check_shape(const mrclip_shape& s, int ld) {
 }
 
 int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
-            const float* scale, const float* bias, int col_begin, int col_end, void* ws, cudaStream_t st) {
+            const float* scale, const float* bias, int col_begin, int col_end, void* ws, void* emat,
+            cudaStream_t st) {
   if (int e = check_shape(sh, ld)) return e;
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
@@ -254,9 +264,12 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   if (col_begin < 0 || col_end > sh.n_cols || col_begin >= col_end) return fail(-1, "bad column range [%d,%d)", col_begin, col_end);
   if (col_begin % granule != 0) return fail(-1, "col_begin=%d not a multiple of the granule %d", col_begin, granule);
   if (col_end != sh.n_cols && col_end % granule != 0) return fail(-1, "col_end=%d not a multiple of the granule %d", col_end, granule);
-  CUtensorMap ma, mb;
+  CUtensorMap ma, mb, me;
   if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
   if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kSBN)) return e;
+  me = mb;
+  if (emat)   // E / G block [m_pad, n_pad] bf16, stored in 32 x 64 boxes
+    if (int e = make_map(&me, emat, f.m_pad, f.n_pad, f.n_pad, 32)) return e;
   TileParams p;
   memset(&p, 0, sizeof p);
   p.m_rows = sh.m_rows;
@@ -282,6 +295,11 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   p.col_c = reinterpret_cast<float*>(wsb + w.col_c);
   p.diag2 = reinterpret_cast<float*>(wsb + w.diag2);
   p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
+  p.sc_part2 = reinterpret_cast<float2*>(wsb + w.sc_part2) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
+  if (emat) {
+    if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWDE, LOSS_CLIP, 256, kSBN>(ma, mb, me, p, st);
+    return launch_tile<MODE_FWDE, LOSS_SIGLIP, 256, kSBN>(ma, mb, me, p, st);
+  }
   if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWD, LOSS_CLIP, 256, kSBN>(ma, mb, mb, p, st);
   return launch_tile<MODE_FWD, LOSS_SIGLIP, 256, kSBN>(ma, mb, mb, p, st);
 }
@@ -340,7 +358,7 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
     long blocks = (total + threads - 1) / threads;
     if (blocks > 148L * 16) blocks = 148L * 16;
     grad_reduce_kernel<<<(int)blocks, threads, 0, st>>>(p.dpart, b.cs, sh.m_rows, sh.d, b.m_pad, b.d_pad, coef,
-                                                        scale, grad_out, d_a, out_dtype, out_ld);
+                                                        scale, grad_out, d_a, out_dtype, out_ld, nullptr, 0, nullptr);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
   }
@@ -377,7 +395,7 @@ int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& 
 // Recompute S for this rank's row block and write G = dLoss/dS (bf16, unscaled) to gmat [m_pad, n_pad].
 int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
                const float* lse2_a, const float* lse2_b, const float* scale, const float* bias, float w_own,
-               float w_oth, void* ws, void* gmat, cudaStream_t st) {
+               float w_oth, void* ws, void* gmat, const int* run_if, cudaStream_t st) {
   if (int e = check_shape(sh, ld)) return e;
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
@@ -408,6 +426,8 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
   p.lse2_b = lse2_b;
   p.g_out = reinterpret_cast<uint16_t*>(gmat);
   p.g_ld = f.n_pad;
+  p.run_if = run_if;
+  p.ent = run_if != nullptr ? 1 : 0;   // the guarded (fallback) run feeds emat_fallback_sums_kernel
   p.sc_part = reinterpret_cast<float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part);
   if (loss_kind == LOSS_CLIP) return launch_tile<MODE_GW, LOSS_CLIP, 256, kSBN>(ma, mb, mb, p, st);
   return launch_tile<MODE_GW, LOSS_SIGLIP, 256, kSBN>(ma, mb, mb, p, st);
@@ -415,9 +435,13 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
 
 // d_out[out_rows, d] = mul * sum_k G(.,.) * F[k, d]; transposed=false contracts G's columns (out rows = G rows),
 // transposed=true contracts G's rows (out rows = G columns; G read as an M-major operand).  F = feat [k_len, ld].
+struct DotArgs {   // optional: dot_out += <d_out, dot_feat> / scale  (d(loss)/d(scale) by homogeneity)
+  const void* dot_feat = nullptr;
+  float* dot_out = nullptr;
+};
 int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* feat, int d, int ld,
                   float coef, const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype,
-                  long out_ld, cudaStream_t st) {
+                  long out_ld, const DotArgs& xf, cudaStream_t st) {
   const int out_rows = transposed ? g_cols : g_rows;
   const int k_len = transposed ? g_rows : g_cols;
   const GemmPlan g = gemm_plan(out_rows, k_len, ld);
@@ -442,7 +466,8 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
   grad_reduce_kernel<<<(int)blocks, 256, 0, st>>>(p.dpart, g.ksplit, out_rows, d, g.m_pad, g.d_pad, coef, scale,
-                                                   grad_out, d_out, out_dtype, out_ld);
+                                                   grad_out, d_out, out_dtype, out_ld,
+                                                   reinterpret_cast<const __nv_bfloat16*>(xf.dot_feat), ld, xf.dot_out);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -528,7 +553,7 @@ int mrclip_transpose_bf16(const void* src, int rows, int cols, long src_ld, void
 
 int mrclip_clip_fwd_tiles(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
                           const float* scale, int col_begin, int col_end, void* ws, void* stream) {
-  return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws,
+  return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws, nullptr,
                  (cudaStream_t)stream);
 }
 
@@ -584,7 +609,7 @@ int mrclip_clip_bwd(const void* a_rows, const void* b_all, const void* bt_all, l
 int mrclip_siglip_fwd(const void* a_rows, const void* b_all, mrclip_shape shape, int ld,
                       const float* scale, const float* bias, void* ws, float* loss, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = run_fwd(LOSS_SIGLIP, a_rows, b_all, shape, ld, scale, bias, 0, shape.n_cols, ws, st)) return e;
+  if (int e = run_fwd(LOSS_SIGLIP, a_rows, b_all, shape, ld, scale, bias, 0, shape.n_cols, ws, nullptr, st)) return e;
   const FwdPlan f = fwd_plan(shape.m_rows, shape.n_cols);
   const WsLayout w = ws_layout(shape.m_rows, shape.n_cols, shape.d);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
@@ -615,7 +640,7 @@ int mrclip_clip_gwrite(const void* a_rows, const void* b_all, mrclip_shape shape
                        const float* grad_out, void* ws, void* gmat, float* d_scale, int accumulate_scalars,
                        int both_directions, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = run_gwrite(LOSS_CLIP, a_rows, b_all, shape, ld, lse2_a, lse2_b, scale, nullptr, w_own, w_oth, ws, gmat, st))
+  if (int e = run_gwrite(LOSS_CLIP, a_rows, b_all, shape, ld, lse2_a, lse2_b, scale, nullptr, w_own, w_oth, ws, gmat, nullptr, st))
     return e;
   return run_scalar_reduce(shape, ws, coef * w_own, both_directions ? coef * w_oth : 0.f, grad_out, d_scale, nullptr,
                            accumulate_scalars, 1, st);
@@ -625,7 +650,7 @@ int mrclip_siglip_gwrite(const void* a_rows, const void* b_all, mrclip_shape sha
                          const float* bias, float coef, const float* grad_out, void* ws, void* gmat, float* d_scale,
                          float* d_bias, int accumulate_scalars, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  if (int e = run_gwrite(LOSS_SIGLIP, a_rows, b_all, shape, ld, nullptr, nullptr, scale, bias, 1.f, 0.f, ws, gmat, st))
+  if (int e = run_gwrite(LOSS_SIGLIP, a_rows, b_all, shape, ld, nullptr, nullptr, scale, bias, 1.f, 0.f, ws, gmat, nullptr, st))
     return e;
   return run_scalar_reduce(shape, ws, coef, coef, grad_out, d_scale, d_bias, accumulate_scalars, 0, st);
 }
@@ -636,7 +661,121 @@ int mrclip_gmat_gemm(int transposed, const void* gmat, mrclip_shape shape, const
   if (int e = check_shape(shape, ld)) return e;
   if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
   return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out,
-                       ws, d_out, out_dtype, out_ld, (cudaStream_t)stream);
+                       ws, d_out, out_dtype, out_ld, DotArgs(), (cudaStream_t)stream);
+}
+
+/* ---- "emat" backend: the forward keeps E (CLIP) / G (SigLIP); no recompute in the backward ------------ */
+int mrclip_clip_fwd_tiles_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                            int col_begin, int col_end, void* ws, void* emat, void* stream) {
+  if (!emat) return fail(-1, "emat is NULL");
+  return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws, emat,
+                 (cudaStream_t)stream);
+}
+
+int mrclip_emat_check(mrclip_shape sh, void* ws, const float* lse2_row, const float* lse2_col, void* stream) {
+  if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
+  cudaStream_t st = (cudaStream_t)stream;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  const int ncb = f.n_pad / 64;
+  float* cbmin = reinterpret_cast<float*>(wsb + w.cbmin);
+  int* flag = reinterpret_cast<int*>(wsb + w.flag);
+  emat_cbmin_kernel<<<ceil_div(ncb * 32, 256), 256, 0, st>>>(lse2_col, ncb, cbmin, flag);
+  emat_check_kernel<<<f.bands, 256, 0, st>>>(reinterpret_cast<const float*>(wsb + w.col_c), lse2_row, sh.m_rows,
+                                             cbmin, ncb, 80.f, flag);
+  g_launches.fetch_add(2);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+const int* mrclip_emat_flag(mrclip_shape sh, void* ws) {
+  if (sh.m_rows <= 0 || sh.n_cols <= 0 || sh.d <= 0 || !ws) return nullptr;
+  return reinterpret_cast<const int*>(reinterpret_cast<uint8_t*>(ws) + ws_layout(sh.m_rows, sh.n_cols, sh.d).flag);
+}
+
+int mrclip_clip_gwrite_if(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* lse2_a,
+                          const float* lse2_b, const float* scale, float w_own, float w_oth, void* ws, void* gmat,
+                          const int* run_if, void* stream) {
+  return run_gwrite(LOSS_CLIP, a_rows, b_all, shape, ld, lse2_a, lse2_b, scale, nullptr, w_own, w_oth, ws, gmat,
+                    run_if, (cudaStream_t)stream);
+}
+
+int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
+                          const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
+                          float* msums, int n_per_rank, int ranks, void* stream) {
+  if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
+  if (!emat || !lse2_row || !lse2_col || !diag2) return fail(-1, "emat_transform: NULL argument");
+  if (msums && skip_if && !scale) return fail(-1, "emat_transform: scale is needed for the fallback sums");
+  if (msums && (n_per_rank <= 0 || ranks <= 0 || (long)n_per_rank * ranks != sh.n_cols))
+    return fail(-1, "emat_transform: n_per_rank * ranks must equal n_cols");
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  const float* colc = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ws) + w.col_c);
+  dim3 grid(ceil_div(f.n_pad, 1024), f.bands);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (msums) {
+    CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks, st));
+    emat_transform_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
+                                                      f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
+                                                      sh.label_offset, w_row, w_col, skip_if, msums, n_per_rank, ranks);
+    if (skip_if) {   // guard raised: the sums come from the exact recompute's partials instead
+      const int items = f.num_rb * f.total_chunks;
+      emat_fallback_sums_kernel<<<ceil_div(items, 256), 256, 0, st>>>(
+          skip_if, reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(ws) + w.sc_part), f.num_rb,
+          f.total_chunks, f.tiles_per_chunk * kSBN, n_per_rank, ranks, scale, msums);
+      g_launches.fetch_add(1);
+    }
+  } else {
+    emat_transform_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
+                                                       f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
+                                                       sh.label_offset, w_row, w_col, skip_if, nullptr, 1, 1);
+  }
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                         const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
+                         const void* dot_feat, float* dot_out, void* stream) {
+  if (int e = check_shape(shape, ld)) return e;
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  DotArgs xf;
+  xf.dot_feat = dot_feat;
+  xf.dot_out = dot_out;
+  return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out,
+                       ws, d_out, out_dtype, out_ld, xf, (cudaStream_t)stream);
+}
+
+int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                        const float* bias, void* ws, float* loss, void* gmat, void* stream) {
+  if (!gmat) return fail(-1, "gmat is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int e = run_fwd(LOSS_SIGLIP, a_rows, b_all, shape, ld, scale, bias, 0, shape.n_cols, ws, gmat, st)) return e;
+  const FwdPlan f = fwd_plan(shape.m_rows, shape.n_cols);
+  const WsLayout w = ws_layout(shape.m_rows, shape.n_cols, shape.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
+                                           (long)f.num_rb * f.total_chunks * kEpiWarps,
+                                           1.f / (float)shape.m_rows, 0.f, nullptr, nullptr, loss, nullptr, 0, 0);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+/* d_scale / d_bias of SigLipLoss from the partials mrclip_siglip_fwd_e left in ws */
+int mrclip_siglip_e_scalars(mrclip_shape shape, void* ws, float coef, const float* grad_out, float* d_scale,
+                            float* d_bias, int accumulate_scalars, void* stream) {
+  if (!d_scale && !d_bias) return 0;
+  const FwdPlan f = fwd_plan(shape.m_rows, shape.n_cols);
+  const WsLayout w = ws_layout(shape.m_rows, shape.n_cols, shape.d);
+  scalar_reduce_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part2),
+      (long)f.num_rb * f.total_chunks * kEpiWarps, coef, coef, grad_out, nullptr, d_scale, d_bias, accumulate_scalars, 0);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 }  // extern "C"

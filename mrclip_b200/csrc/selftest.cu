@@ -298,6 +298,86 @@ static void check_clip(int N, int D, int W, float s, float corr) {
     report("gmat d_scale per rank", rel_err(dS, hds), 1e-2);
     cudaFree(gmat);
   }
+  // ---- emat backend: forward keeps E, the GEMMs rebuild G in shared memory; dT = sum over ranks of G_r^T . I_r
+  {
+    void* emat;
+    float *dTp, *tmp_m, *tmp_l, *tmp_lr, *tmp_dg, *msums;
+    CK(cudaMalloc(&msums, (size_t)2 * W * W * 4));
+    CK(cudaMalloc(&emat, mrclip_gmat_bytes(n, N)));
+    CK(cudaMemset(emat, 0xff, mrclip_gmat_bytes(n, N)));
+    CK(cudaMalloc(&dTp, (size_t)N * D * 4));
+    CK(cudaMalloc(&tmp_m, (size_t)N * 4));
+    CK(cudaMalloc(&tmp_l, (size_t)N * 4));
+    CK(cudaMalloc(&tmp_lr, (size_t)N * 4));
+    CK(cudaMalloc(&tmp_dg, (size_t)N * 4));
+    std::vector<double> accT((size_t)N * D, 0.0);
+    std::vector<float> hp((size_t)N * D);
+    int flags = 0;
+    for (int r = 0; r < W; ++r) {
+      mrclip_shape sh = {n, N, D, r * n};
+      const char* ai = (const char*)d.Ibf + (size_t)r * n * d.ld * 2;
+      MR(mrclip_clip_fwd_tiles_e(ai, d.Tbf, sh, d.ld, d.scale, 0, N, d.ws, emat, 0));
+      MR(mrclip_clip_fwd_reduce(sh, d.ws, tmp_lr, tmp_m, tmp_l, tmp_dg, 0));
+      MR(mrclip_emat_check(sh, d.ws, lse2_row_all + r * n, lse2_col_all, 0));
+      const int* flag = mrclip_emat_flag(sh, d.ws);
+      MR(mrclip_clip_gwrite_if(ai, d.Tbf, sh, d.ld, lse2_row_all + r * n, lse2_col_all, d.scale, 1.f, 1.f, d.ws, emat,
+                               flag, 0));
+      CK(cudaMemset(dscale + r, 0, 4));
+      MR(mrclip_emat_transform(sh, d.ws, emat, lse2_row_all + r * n, lse2_col_all, diag2 + r * n, d.scale, 1.f, 1.f, flag,
+                               msums + 2 * W * r, n, W, 0));
+      MR(mrclip_gmat_gemm_dot(0, emat, sh, d.Tbf, d.ld, (float)coef, d.scale, d.gout, d.ws, dA + (size_t)r * n * D,
+                              MRCLIP_DT_F32, D, ai, dscale + r, 0));
+      MR(mrclip_gmat_gemm(1, emat, sh, ai, d.ld, (float)coef, d.scale, d.gout, d.ws, dTp, MRCLIP_DT_F32, D, 0));
+      CK(cudaDeviceSynchronize());
+      int hf = 0;
+      CK(cudaMemcpy(&hf, flag, 4, cudaMemcpyDeviceToHost));
+      flags += hf;
+      CK(cudaMemcpy(hI.data() + (size_t)r * n * D, dA + (size_t)r * n * D, (size_t)n * D * 4, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(hp.data(), dTp, (size_t)N * D * 4, cudaMemcpyDeviceToHost));
+      for (size_t k = 0; k < accT.size(); ++k) accT[k] += hp[k];
+    }
+    for (size_t k = 0; k < accT.size(); ++k) hT[k] = (float)accT[k];
+    report("emat dI", rel_err(dI, hI), 1e-2);
+    report("emat dT (sum of rank partials)", rel_err(dT, hT), 1e-2);
+    if (W == 1) {
+      CK(cudaMemcpy(hds.data(), dscale, W * 4, cudaMemcpyDeviceToHost));
+      report("emat d_scale (<dI,I>/s)", rel_err(dS, hds), 1e-2);
+      printf("    ds[0] = %.6e (ref %.6e)\n", hds[0], dS[0]);
+    }
+    {   // d_scale per rank from the split sums: row r of the Prow matrix + column r of the Pcol matrix
+      std::vector<float> hm((size_t)2 * W * W);
+      CK(cudaMemcpy(hm.data(), msums, hm.size() * 4, cudaMemcpyDeviceToHost));
+      std::vector<float> ds2(W);
+      for (int r = 0; r < W; ++r) {
+        double a = 0;
+        for (int c2 = 0; c2 < W; ++c2) a += hm[(size_t)2 * W * r + c2];            // Prow log2 Prow, my rows, all column ranks
+        for (int q = 0; q < W; ++q) a += hm[(size_t)2 * W * q + W + r];            // Pcol log2 Pcol, all row ranks, my columns
+        // scale * dL_r/dscale = L_r + ln2/(2n) * (negative entropies)
+        ds2[r] = (float)((L[r] + 0.6931471805599453 * coef * a) / s);
+      }
+      {   // the sums themselves against fp64 (single rank view: totals over all ranks)
+        double hr = 0, hc = 0, gr = 0, gc = 0;
+        for (int i = 0; i < N; ++i)
+          for (int j = 0; j < N; ++j) {
+            const double sij = s * C[(size_t)i * N + j];
+            const double lpr = (sij - lr[i]) * 1.4426950408889634, lpc = (sij - lc[j]) * 1.4426950408889634;
+            hr += exp2(lpr) * lpr;
+            hc += exp2(lpc) * lpc;
+          }
+        for (int q = 0; q < W; ++q)
+          for (int c2 = 0; c2 < W; ++c2) {
+            gr += hm[(size_t)2 * W * q + c2];
+            gc += hm[(size_t)2 * W * q + W + c2];
+          }
+        printf("    sum P log2 P: rows %.6f (ref %.6f)  cols %.6f (ref %.6f)\n", gr, hr, gc, hc);
+      }
+      report("emat d_scale per rank (split sums)", rel_err(dS, ds2), 1e-2);
+      printf("    ds[0] = %.6e (ref %.6e)\n", ds2[0], dS[0]);
+    }
+    printf("    emat guard flag raised on %d of %d ranks\n", flags, W);
+    cudaFree(msums);
+    cudaFree(emat); cudaFree(dTp); cudaFree(tmp_m); cudaFree(tmp_l); cudaFree(tmp_lr); cudaFree(tmp_dg);
+  }
   cudaFree(lse2_row_all); cudaFree(col_m); cudaFree(col_l); cudaFree(lse2_col_all); cudaFree(diag2);
   cudaFree(loss); cudaFree(dscale); cudaFree(dA);
   teardown(d);
@@ -459,6 +539,43 @@ static void time_shape(int N, int D, int reps) {
            ta, tb, flop / tb * 1e-9, tc, tf + ta + tb + tc, N / (tf + ta + tb + tc) * 1e-3,
            3 * flop / (tf + ta + tb + tc) * 1e-9);
     cudaFree(gmat);
+  }
+  {
+    void* emat;
+    CK(cudaMalloc(&emat, mrclip_gmat_bytes(N, N)));
+    cudaEvent_t g0, g1, g2, g3;
+    cudaEventCreate(&g0); cudaEventCreate(&g1); cudaEventCreate(&g2); cudaEventCreate(&g3);
+    float ta = 0, tb = 0, tc = 0;
+    const int* flag = mrclip_emat_flag(sh, d.ws);
+    float* msums;
+    CK(cudaMalloc(&msums, 8));
+    const bool wsum_on = getenv("SELFTEST_NO_WSUM") == nullptr;
+    for (int it = 0; it < reps + 2; ++it) {
+      CK(cudaEventRecord(g0));
+      MR(mrclip_clip_fwd_tiles_e(d.Ibf, d.Tbf, sh, d.ld, d.scale, 0, N, d.ws, emat, 0));
+      MR(mrclip_clip_fwd_reduce(sh, d.ws, lse2_row, col_m, col_l, diag2, 0));
+      MR(mrclip_lse2_merge(col_m, col_l, 1, N, N, lse2_col, 0));
+      MR(mrclip_clip_loss(lse2_row, lse2_col, diag2, N, 0, loss, 0));
+      CK(cudaEventRecord(g1));
+      MR(mrclip_emat_check(sh, d.ws, lse2_row, lse2_col, 0));
+      MR(mrclip_clip_gwrite_if(d.Ibf, d.Tbf, sh, d.ld, lse2_row, lse2_col, d.scale, 1.f, 1.f, d.ws, emat, flag, 0));
+      MR(mrclip_emat_transform(sh, d.ws, emat, lse2_row, lse2_col, diag2, d.scale, 1.f, 1.f, flag, wsum_on ? msums : nullptr, N, 1, 0));
+      CK(cudaEventRecord(g2));
+      MR(mrclip_gmat_gemm_dot(0, emat, sh, d.Tbf, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, d.Ibf,
+                              dscale, 0));
+      MR(mrclip_gmat_gemm(1, emat, sh, d.Ibf, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, 0));
+      CK(cudaEventRecord(g3));
+      CK(cudaEventSynchronize(g3));
+      float a, b, c;
+      cudaEventElapsedTime(&a, g0, g1);
+      cudaEventElapsedTime(&b, g1, g2);
+      cudaEventElapsedTime(&c, g2, g3);
+      if (it >= 2) { ta += a; tb += b; tc += c; }
+    }
+    ta /= reps; tb /= reps; tc /= reps;
+    printf("  emat: fwd+E %.3f ms | check+transform %.3f ms (%.0f) | 2 gemms %.3f ms | total %.3f ms -> %.2f Mpairs/s, %.1f TF/s algorithmic\n",
+           ta, tb, flop / tb * 1e-9, tc, ta + tb + tc, N / (ta + tb + tc) * 1e-3, 3 * flop / (ta + tb + tc) * 1e-9);
+    cudaFree(emat);
   }
   teardown(d);
 }

@@ -31,7 +31,12 @@ constexpr int kThreads = 64 + 32 * kEpiWarps;
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2 };  // GW: recompute S, write the bf16 gradient tile G to global
+// GW:   recompute S, write the bf16 gradient tile G to global.
+// FWDE: forward that also writes E = exp2(S2 - c) (bf16, c = the 32x64 sub-tile maximum it already tracks for the
+//       column sums) so that the backward never recomputes S: G = E * (2^(c-lse_row) + 2^(c-lse_col)) is formed
+//       on the fly inside the gradient GEMMs (gemm_kernel<.., XF>).  SigLIP has no normaliser, so its FWDE writes
+//       G = sigmoid(z) - delta directly.
+enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2, MODE_FWDE = 3 };
 enum : int { LOSS_CLIP = 0, LOSS_SIGLIP = 1 };
 
 struct TileParams {
@@ -54,10 +59,11 @@ struct TileParams {
   // FWD (clip)
   float2* row_part;     // [slots][m_pad]   (max2, sum)
   float* col_l;         // [bands][n_pad]
-  float* col_c;         // [bands][n_pad/64]
+  float* col_c;         // [bands][n_pad/64]  sub-tile reference (max2) of the column sums and of E
   float* diag2;         // [m_pad]  positive logit in log2 units
   // FWD (siglip) / BWD scalar partials
   float2* sc_part;      // [num_items * 8]
+  float2* sc_part2;     // [num_items * 8]  FWDE siglip: (sum G*C, sum G)
   // BWD
   const float* lse2_a;  // [m_rows]   own-direction LSE of each A row (log2 units)
   const float* lse2_b;  // [n_pad]    other-direction LSE of each B row, +inf padded
@@ -65,6 +71,8 @@ struct TileParams {
   // GW
   uint16_t* g_out;      // bf16 [m_pad][g_ld]
   long g_ld;
+  const int* run_if;    // optional device flag: the kernel returns at once when *run_if == 0
+  int ent;              // GW clip: scalar partials become (sum P_own log2 P_own, sum P_oth log2 P_oth)
 };
 
 template <int LEN, int OFF>
@@ -106,7 +114,10 @@ struct TileCfg {
   // (fetched before the accumulator wait, so the global-load latency is off the critical path)
   static constexpr bool kLseSmem = (MODE == MODE_GW && LOSS == LOSS_CLIP);
   static constexpr int kLseBytes = kLseSmem ? kEpiWarps * (BN / 2) * 4 : 0;
-  static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kLseBytes + kNumBars * 8 + 16 + 1024;
+  // FWDE: one 32x64 bf16 staging tile per epilogue warp (128-byte swizzled rows) for the TMA store of E
+  static constexpr bool kEOut = (MODE == MODE_FWDE);
+  static constexpr int kEBytes = kEOut ? kEpiWarps * 4096 : 0;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kLseBytes + kEBytes + kNumBars * 8 + 16 + 1024;
 };
 
 template <int MODE, int LOSS, int DC, int BN>
@@ -122,13 +133,16 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   constexpr uint32_t IDESC_S = make_idesc_bf16(kBM, BN);
   constexpr uint32_t IDESC_D = make_idesc_bf16(kBM, DN);
 
+  if (p.run_if != nullptr && __ldg(p.run_if) == 0) return;   // grid-uniform: nobody touches a barrier or TMEM
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_base = smem_u32(smem);
   const uint32_t g_base = stage_base + STAGES * kStageBytes;
   const uint32_t lse_smem = g_base + Cfg::kGBytes;
-  uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes + Cfg::kLseBytes;
+  const uint32_t e_smem = lse_smem + Cfg::kLseBytes;   // 1024-byte aligned (stages and G are multiples of 1024)
+  uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes + Cfg::kLseBytes + Cfg::kEBytes;
+  constexpr bool kFwd = (MODE == MODE_FWD || MODE == MODE_FWDE);
   const uint32_t bar_base = smem_u32(bar_ptr);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + Cfg::kNumBars * 8);
 
@@ -147,7 +161,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (MODE == MODE_BWD) tma_prefetch_desc(&tmBt);
+    if (MODE == MODE_BWD || MODE == MODE_FWDE) tma_prefetch_desc(&tmBt);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -349,9 +363,9 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int label_w0 = rb * kBM + q * 32 + p.label_offset;  // label of lane 0 (warp uniform)
 
       float m_run = -CUDART_INF_F, l_run = 0.f;  // FWD clip: running row (max2, sum)
-      float acc0 = 0.f, acc1 = 0.f;              // scalar partials (loss | ds, db)
+      float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // scalar partials (loss | ds, db)
       float lr2 = CUDART_INF_F;
-      if (MODE != MODE_FWD && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
+      if (!kFwd && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
 
       for (int t = t0; t < t1; ++t) {
         const uint32_t buf = s_use % NSB, use = s_use / NSB;
@@ -391,7 +405,29 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool ragged = (col_base + 64 > p.n_cols);  // warp uniform
         const bool diag_here = (label_w0 + 31 >= col_base) && (label_w0 < col_base + 64);
 
-        if (MODE == MODE_FWD && LOSS == LOSS_CLIP) {
+        // FWDE: pack 64 fp32 values of this thread's row to bf16, stage them (swizzled) and TMA-store the warp's
+        // 32 x 64 tile to e_out[rb*128 + q*32 .., col_base ..]  (tmBt is the store map in this mode)
+        auto store_e = [&](const float (&e)[64]) {
+          const uint32_t stg = e_smem + (warp - 2) * 4096;
+          if (lane == 0) bulk_wait_read0();   // the previous tile of this warp has left the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int ck = 0; ck < 8; ++ck) {
+            uint4 o;
+            o.x = pack_bf16x2(e[ck * 8 + 0], e[ck * 8 + 1]);
+            o.y = pack_bf16x2(e[ck * 8 + 2], e[ck * 8 + 3]);
+            o.z = pack_bf16x2(e[ck * 8 + 4], e[ck * 8 + 5]);
+            o.w = pack_bf16x2(e[ck * 8 + 6], e[ck * 8 + 7]);
+            sts_u4(stg + lane * 128 + ((static_cast<uint32_t>(ck) ^ (lane & 7)) << 4), o);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmBt, stg, col_base, rb * kBM + q * 32);
+            bulk_commit();
+          }
+        };
+        if (kFwd && LOSS == LOSS_CLIP) {
           float v[64];
 #pragma unroll
           for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(raw[c]) * sl;
@@ -421,6 +457,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             v[c] = ex2f(v[c] - cw);
             rowsum += v[c];
           }
+          if (Cfg::kEOut) store_e(v);
           const float mnew = fmaxf(m_run, cw);
           l_run = l_run * ex2f(m_run - mnew) + rowsum * ex2f(cw - mnew);
           m_run = mnew;
@@ -433,24 +470,48 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           *reinterpret_cast<float2*>(p.col_l + (size_t)band * p.n_pad + col_base + 2 * lane) =
               make_float2(v[0], v[1]);
           if (lane == 0) p.col_c[(size_t)band * (p.n_pad / 64) + col_base / 64] = cw;
-        } else if (MODE == MODE_FWD && LOSS == LOSS_SIGLIP) {
+        } else if (kFwd && LOSS == LOSS_SIGLIP) {
           float part = 0.f;
+          float gv[64];
+          float dsum = 0.f, bsum = 0.f;
 #pragma unroll
           for (int c = 0; c < 64; ++c) {
             const float a = __uint_as_float(raw[c]);
             const float z = fmaf(a, s, bias);
             const float u = fmaf(a, sl, b2);
-            float sp = fmaxf(z, 0.f) + log1p_from_exp(ex2f(-fabsf(u)));
-            if (ragged && (col_base + c >= p.n_cols)) sp = 0.f;
+            const float e = ex2f(-fabsf(u));
+            float sp = fmaxf(z, 0.f) + log1p_from_exp(e);
+            const bool dead = (ragged && (col_base + c >= p.n_cols)) || !row_valid;
+            if (dead) sp = 0.f;
             part += sp;
+            if (Cfg::kEOut) {
+              float g = (u >= 0.f ? 1.f : e) * rcpf(1.f + e);   // sigmoid(z)
+              if (dead) g = 0.f;
+              gv[c] = g;
+              dsum = fmaf(g, a, dsum);
+              bsum += g;
+            }
           }
           if (diag_here) {
             const int idx = label - col_base;
 #pragma unroll
             for (int c = 0; c < 64; ++c)
-              if (c == idx) part -= fmaf(__uint_as_float(raw[c]), s, bias);
+              if (c == idx && row_valid) {
+                const float a = __uint_as_float(raw[c]);
+                part -= fmaf(a, s, bias);
+                if (Cfg::kEOut) {
+                  gv[c] -= 1.f;
+                  dsum -= a;
+                  bsum -= 1.f;
+                }
+              }
           }
-          if (row_valid) acc0 += part;
+          acc0 += part;
+          if (Cfg::kEOut) {
+            store_e(gv);
+            acc1 += dsum;
+            acc2 += bsum;
+          }
         } else {
           // ------------------------------------------------------------- BWD / GW: build G
           const uint32_t gb = g_use & 1, guse = g_use >> 1;
@@ -479,8 +540,13 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const float p_own = ex2f(tt - lr2);
                 const float p_oth = ex2f(tt - lb[j]);
                 g[j] = p.w_own * p_own + p.w_oth * p_oth;
-                dsum = fmaf(p_own, a, dsum);
-                if (MODE == MODE_GW) bsum = fmaf(p_oth, a, bsum);   // other-direction term of d_scale
+                if (MODE == MODE_GW && p.ent) {   // negative entropies (lse = +inf on dead rows / columns: P = 0)
+                  dsum = fmaf(p_own, p_own > 0.f ? tt - lr2 : 0.f, dsum);
+                  bsum = fmaf(p_oth, p_oth > 0.f ? tt - lb[j] : 0.f, bsum);
+                } else {
+                  dsum = fmaf(p_own, a, dsum);
+                  if (MODE == MODE_GW) bsum = fmaf(p_oth, a, bsum);   // other-direction term of d_scale
+                }
               }
             } else {
 #pragma unroll
@@ -512,8 +578,10 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                   const float a = __uint_as_float(raw[ck * 8 + j]);
                   if (LOSS == LOSS_CLIP) {
                     g[j] -= (p.w_own + p.w_oth);
-                    dsum -= a;
-                    if (MODE == MODE_GW) bsum -= a;
+                    if (!(MODE == MODE_GW && p.ent)) {
+                      dsum -= a;
+                      if (MODE == MODE_GW) bsum -= a;
+                    }
                   } else {
                     g[j] -= 1.f;
                     dsum -= a;
@@ -551,12 +619,18 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }  // tiles
 
       // ------------------------------------------------------------------ item outputs
-      if (MODE == MODE_FWD && LOSS == LOSS_CLIP) {
+      if (kFwd && LOSS == LOSS_CLIP) {
         const int slot = (p.chunk_base + chunk) * 2 + h;
         p.row_part[(size_t)slot * p.m_pad + grow] = make_float2(m_run, l_run);
-      } else if (MODE == MODE_FWD) {
+      } else if (kFwd) {
         const float tot = warp_sum(acc0);
         if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(tot, 0.f);
+        if (Cfg::kEOut) {   // SigLIP: the d_scale / d_bias partials ride along (second float2 plane)
+          const float t1s = warp_sum(acc1);
+          const float t2s = warp_sum(acc2);
+          if (lane == 0)
+            p.sc_part2[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(t1s, t2s);
+        }
       } else if (MODE == MODE_GW) {
         const float t0s = warp_sum(acc0);
         const float t1s = warp_sum(acc1);
@@ -595,6 +669,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(t0s, t1s);
       }
     }  // items
+    if (Cfg::kEOut && lane == 0) bulk_wait_read0();
   }
 
   tc_fence_before();

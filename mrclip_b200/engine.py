@@ -127,6 +127,44 @@ class CudaEngine:
                                               _DT[d_out.dtype], d_out.stride(0), self._stream()))
 
 
+    # ---- "emat" backend: the forward keeps E (CLIP) or G (SigLIP); the backward never recomputes S ---------
+    def clip_fwd_tiles_e(self, a_rows, b_all, shape, scale, col_begin, col_end, ws, emat):
+        _cabi.check(self.lib.mrclip_clip_fwd_tiles_e(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                     scale.data_ptr(), col_begin, col_end, ws.data_ptr(),
+                                                     emat.data_ptr(), self._stream()))
+
+    def emat_to_gmat(self, a_rows, b_all, shape, lse2_row, lse2_col, diag2, scale, w_row, w_col, ws, emat,
+                     msums=None, n_per_rank=0, ranks=1):
+        """E -> G in place.  The guard decides on the device between the one-pass rewrite (normal) and the exact
+        recompute of G (when a flushed E entry could carry gradient); exactly one of the two kernels does work.
+        msums (float32 [2, ranks], optional) receives the d_logit_scale sums split by column owner."""
+        st = self._stream()
+        _cabi.check(self.lib.mrclip_emat_check(shape, ws.data_ptr(), lse2_row.data_ptr(), lse2_col.data_ptr(), st))
+        flag = self.lib.mrclip_emat_flag(shape, ws.data_ptr())
+        _cabi.check(self.lib.mrclip_clip_gwrite_if(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                   lse2_row.data_ptr(), lse2_col.data_ptr(), scale.data_ptr(),
+                                                   w_row, w_col, ws.data_ptr(), emat.data_ptr(), flag, st))
+        _cabi.check(self.lib.mrclip_emat_transform(shape, ws.data_ptr(), emat.data_ptr(), lse2_row.data_ptr(),
+                                                   lse2_col.data_ptr(), diag2.data_ptr(), scale.data_ptr(), w_row,
+                                                   w_col, flag, _ptr(msums), n_per_rank, ranks, st))
+
+    def gmat_gemm_dot(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out, dot_feat, dot_out):
+        """gmat_gemm that also accumulates <d_out, dot_feat>/scale into dot_out (= d loss / d logit_scale)."""
+        _cabi.check(self.lib.mrclip_gmat_gemm_dot(int(transposed), gmat.data_ptr(), shape, feat.data_ptr(),
+                                                  feat.shape[1], coef, scale.data_ptr(), _ptr(grad_out), ws.data_ptr(),
+                                                  d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0),
+                                                  _ptr(dot_feat), _ptr(dot_out), self._stream()))
+
+    def siglip_fwd_e(self, a_rows, b_all, shape, scale, bias, ws, loss, gmat):
+        _cabi.check(self.lib.mrclip_siglip_fwd_e(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                 scale.data_ptr(), _ptr(bias), ws.data_ptr(), loss.data_ptr(),
+                                                 gmat.data_ptr(), self._stream()))
+
+    def siglip_e_scalars(self, shape, ws, coef, grad_out, d_scale, d_bias, accumulate):
+        _cabi.check(self.lib.mrclip_siglip_e_scalars(shape, ws.data_ptr(), coef, _ptr(grad_out), _ptr(d_scale),
+                                                     _ptr(d_bias), int(accumulate), self._stream()))
+
+
 _default_engine = None
 
 

@@ -4,16 +4,21 @@ Same constructor and call signatures as the reference (``src/open_clip/loss.py``
 ``gather_features`` :21-65, ``ClipLoss`` :68-139, ``SigLipLoss`` :314-448), so
 ``open_clip.factory.create_loss`` (factory.py:432-503) and ``train_one_epoch`` (train.py:128)
 use it unchanged.  Behind the signatures the N x N logit matrix never exists: the forward runs the
-tcgen05 tile kernel with a fused online log-sum-exp, the backward re-runs the tiles and contracts
-the gradient tile in TMEM (``csrc/tile_kernel.cuh``).
+tcgen05 tile kernel with a fused online log-sum-exp (``csrc/tile_kernel.cuh``) and keeps only the bf16
+exponentials E of this rank's row block; the backward rescales E into the gradient of the logits in one
+HBM pass and contracts it twice with plain tcgen05 GEMMs (``csrc/gemm_kernel.cuh``): three N x N x D
+contractions per step, the algorithmic minimum ("emat" backend).  The older backends (``MRCLIP_BWD=gmat``:
+recompute S and write G, 4-5 contractions; ``fused``: O(N*D) memory, 7) remain selectable and tested.
 
 Multi-rank decomposition (one process per GPU, ``torch.distributed`` / NCCL for plumbing only):
 rank r owns rows [r*n, (r+1)*n) of both modalities.  Forward: all-gather of the bf16-packed
 features, row-block tiles -> exact row LSE + per-column partial (max,sum) -> one small all-gather
-of those statistics.  Backward: two row passes, (I_r vs T_all) -> dI_r and (T_r vs I_all) -> dT_r,
-each complete on its own rank, so no gradient collective is needed at all: the reference's
-reduce-scatter of W full copies (torch/distributed/nn/functional.py:343-347) disappears.  The
-per-rank values reproduce the reference's conventions exactly:
+of those statistics.  Backward (emat): dI_r = G_r . T_all is complete on its rank; the text gradient is
+the sum over ranks of G_q^T . I_q, i.e. one reduce-scatter of [N, D] fp32 partials that runs while the
+dI GEMM computes -- it replaces the reference's reduce-scatter of W full copies per modality
+(torch/distributed/nn/functional.py:343-347).  (gmat / fused backends: a second row pass T_r vs I_all
+instead, no gradient collective.)  The per-rank values reproduce the reference's conventions exactly
+(SURVEY.md §3a):
 
   (local_loss, gather_with_grad)   loss on rank r     d features                d logit_scale
   (F, F)                           L_global           1/(2N) * (Pr + Pc - 2d)   global
@@ -128,6 +133,9 @@ class _Workspace:
         self.in_use = False
         self.transposed = False
         self.gmat = None
+        self.dt_partial = None
+        self.msums = torch.zeros((2, world), dtype=f32, device=device)
+        self.has_emat = False
 
     def gmat_buffer(self, eng):
         """bf16 scratch for the materialised gradient block G (n x N), allocated on first use."""
@@ -136,18 +144,28 @@ class _Workspace:
             self.gmat = torch.empty(max(nbytes // 2, 8), dtype=torch.bfloat16, device=self.img_all.device)
         return self.gmat
 
+    def dt_partial_buffer(self):
+        """fp32 [N, d] partial text gradient of this rank's row block (reduce-scattered), world > 1 only."""
+        if self.dt_partial is None:
+            self.dt_partial = torch.empty((self.N, self.d), dtype=torch.float32, device=self.img_all.device)
+        return self.dt_partial
+
+
+def _backend(eng, ws):
+    """MRCLIP_BWD = emat | gmat | fused | auto.  auto: emat (or gmat) while the n x N bf16 block stays under
+    MRCLIP_GMAT_MAX_GIB (16), else fused."""
+    mode = os.environ.get("MRCLIP_BWD", "auto").lower()
+    if mode in ("emat", "gmat", "fused"):
+        return mode
+    limit = float(os.environ.get("MRCLIP_GMAT_MAX_GIB", "16")) * 2 ** 30
+    return "emat" if int(eng.gmat_bytes(ws.n, ws.N)) <= limit else "fused"
+
 
 def _use_gmat(eng, ws):
     """Backward backend: 'gmat' writes G = dLoss/dS once (bf16, n x N) and runs plain GEMMs (4-5 GEMM units
     per step); 'fused' keeps O(N*D) memory but recomputes S per 384-wide slice of D (7 units).  MRCLIP_BWD
     = gmat | fused | auto (default: gmat while the block stays under MRCLIP_GMAT_MAX_GIB, 16 GiB)."""
-    mode = os.environ.get("MRCLIP_BWD", "auto").lower()
-    if mode == "fused":
-        return False
-    if mode == "gmat":
-        return True
-    limit = float(os.environ.get("MRCLIP_GMAT_MAX_GIB", "16")) * 2 ** 30
-    return int(eng.gmat_bytes(ws.n, ws.N)) <= limit
+    return _backend(eng, ws) in ("gmat", "emat")
 
 
 class _WorkspacePool:
@@ -163,6 +181,7 @@ class _WorkspacePool:
             if not w.in_use:
                 w.in_use = True
                 w.transposed = False
+                w.has_emat = False
                 return w
         w = _Workspace(eng, device, n, world, d)
         w.in_use = True
@@ -238,7 +257,13 @@ class _ClipLossFn(torch.autograd.Function):
         rows = slice(rank * n, (rank + 1) * n)
 
         _gather_packed(eng, ws, image_features, text_features, rank, world)
-        eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
+        # (local_loss, not gather_with_grad) gives the two gradients different G matrices; it keeps the gmat path
+        split_g = world > 1 and module.local_loss and not module.gather_with_grad
+        if any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g:
+            eng.clip_fwd_tiles_e(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
+            ws.has_emat = True
+        else:
+            eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
         col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
         eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
         if world > 1:
@@ -250,6 +275,7 @@ class _ClipLossFn(torch.autograd.Function):
             ws.lse2_row_all[:N].copy_(row_lse)
         loss = torch.empty((1,), dtype=torch.float32, device=device)
         eng.clip_loss(ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2, n, rank * n, loss)
+        ctx.loss_local = loss.clone() if (world > 1 and not module.local_loss) else loss
         if world > 1 and not module.local_loss:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
             loss /= world
@@ -283,7 +309,44 @@ class _ClipLossFn(torch.autograd.Function):
         # d logit_scale always uses 1/(2n) per rank; global modes average it over ranks below
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
-        if _use_gmat(eng, ws):
+        ds_done = False
+        if ws.has_emat:
+            gmat = ws.gmat_buffer(eng)
+            # d logit_scale: one rank with a large block takes <dI, I>/scale from the GEMM's reduce (free; the bf16
+            # rounding of G averages out); otherwise the rescale pass accumulates the softmax entropies, which is
+            # exact per rank and insensitive to that rounding
+            use_dot = world == 1 and n * N >= (1 << 22)
+            msums = ws.msums if (need_s and not use_dot) else None
+            eng.emat_to_gmat(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2,
+                             ctx.scale, 1.0, 1.0, ws.scratch, gmat, msums, n, world)
+            if world == 1:
+                eng.gmat_gemm_dot(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img,
+                                  ws.img_all[rows] if (need_s and use_dot) else None, ds)
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
+                if need_s and not use_dot:
+                    ds = (gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ws.msums.sum())
+                    ds_done = True
+            else:
+                # text gradient: every rank holds G_q^T . I_q for all N text rows; the owner sums them
+                part = ws.dt_partial_buffer()
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, part)
+                dt32 = torch.empty((n, d), dtype=torch.float32, device=device)
+                work = dist.reduce_scatter_tensor(dt32, part, op=dist.ReduceOp.SUM, async_op=True)
+                eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+                if need_s:
+                    # scale * dL_r/dscale = L_r + ln2/(2n) * (sum P log2 P over my rows, row softmax, all columns
+                    #                                         + over my columns, column softmax, all rows)
+                    colsum = ws.msums[1].clone()
+                    dist.all_reduce(colsum, op=dist.ReduceOp.SUM)
+                    ent = ws.msums[0].sum() + colsum[rank]
+                    ds = ((gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ent)).reshape(1)
+                    if not module.local_loss:
+                        dist.all_reduce(ds, op=dist.ReduceOp.SUM)
+                        ds = ds / world
+                    ds_done = True
+                work.wait()
+                d_txt.copy_(dt32)
+        elif _use_gmat(eng, ws):
             gmat = ws.gmat_buffer(eng)
             # image rows vs all texts: G block of this rank's rows -> dI_r
             eng.clip_gwrite(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ctx.scale,
@@ -303,11 +366,12 @@ class _ClipLossFn(torch.autograd.Function):
             eng.clip_bwd(ws.txt_all[rows], ws.img_all, ws.img_t, shape, ws.lse2_col_all[rows], ws.lse2_row_all,
                          ctx.scale, 1.0, w_oth, coef, gout, ws.scratch, d_txt, ds, True)
         if need_s:
-            if coef != 0.5 / n:
-                ds *= (0.5 / n) / coef
-            if world > 1 and not module.local_loss:
-                dist.all_reduce(ds, op=dist.ReduceOp.SUM)
-                ds /= world
+            if not ds_done:
+                if coef != 0.5 / n:
+                    ds *= (0.5 / n) / coef
+                if world > 1 and not module.local_loss:
+                    dist.all_reduce(ds, op=dist.ReduceOp.SUM)
+                    ds /= world
             shp, dt = ctx.scale_meta
             d_scale = ds.reshape(shp).to(dt)
         module._pool.give_back(ws)
@@ -388,7 +452,12 @@ class _SigLipLossFn(torch.autograd.Function):
         rows = slice(rank * n, (rank + 1) * n)
         _gather_packed(eng, ws, image_features, text_features, rank, world)
         loss = torch.empty((1,), dtype=torch.float32, device=device)
-        eng.siglip_fwd(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss)
+        if any(ctx.needs_input_grad) and _backend(eng, ws) == "emat":
+            # no normaliser: the forward can store G = sigmoid(z) - delta itself
+            eng.siglip_fwd_e(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss, ws.gmat_buffer(eng))
+            ws.has_emat = True
+        else:
+            eng.siglip_fwd(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss)
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
         ctx.scale, ctx.bias = scale, bias
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
@@ -416,7 +485,21 @@ class _SigLipLossFn(torch.autograd.Function):
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
         # every rank's loss touches T_r: the column block gives the summed (W x) text gradient directly
-        if _use_gmat(eng, ws):
+        if ws.has_emat:
+            gmat = ws.gmat_buffer(eng)
+            eng.siglip_e_scalars(shape, ws.scratch, coef, gout, ds, db, False)
+            if world == 1:
+                eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
+            else:
+                part = ws.dt_partial_buffer()
+                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, part)
+                dt32 = torch.empty((n, d), dtype=torch.float32, device=device)
+                work = dist.reduce_scatter_tensor(dt32, part, op=dist.ReduceOp.SUM, async_op=True)
+                eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+                work.wait()
+                d_txt.copy_(dt32)
+        elif _use_gmat(eng, ws):
             gmat = ws.gmat_buffer(eng)
             eng.siglip_gwrite(ws.img_all[rows], ws.txt_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch, gmat,
                               ds, db, False)

@@ -198,6 +198,61 @@ class StandInEngine:
         out = (g.t() if transposed else g) @ feat.double()
         d_out.copy_((coef * s * go * out)[:, :d_out.shape[1]].to(d_out.dtype))
 
+    # ---- emat backend ------------------------------------------------------------------------
+    def clip_fwd_tiles_e(self, a_rows, b_all, shape, scale, col_begin, col_end, ws, emat):
+        self.clip_fwd_tiles(a_rows, b_all, shape, scale, col_begin, col_end, ws)
+        self.calls[-1] = "clip_fwd_tiles_e"
+        # what the kernel leaves behind is a function of the logits only; keep a marker so a stale block is caught
+        self.state[("emat", emat.data_ptr())] = (a_rows.data_ptr(), shape.label_offset)
+
+    def emat_to_gmat(self, a_rows, b_all, shape, lse2_row, lse2_col, diag2, scale, w_row, w_col, ws, emat,
+                     msums=None, n_per_rank=0, ranks=1):
+        self.calls.append("emat_to_gmat")
+        assert self.state.pop(("emat", emat.data_ptr())) == (a_rows.data_ptr(), shape.label_offset), "stale E block"
+        s = float(scale.item())
+        t2 = s * self._cos(a_rows, b_all) * LOG2E
+        p_row = torch.exp2(t2 - lse2_row[:shape.m_rows].double()[:, None])
+        p_col = torch.exp2(t2 - lse2_col[:shape.n_cols].double()[None, :])
+        idx = torch.arange(shape.m_rows)
+        g = w_row * p_row + w_col * p_col
+        g[idx, idx + shape.label_offset] -= (w_row + w_col)
+        self._gview(emat, shape).copy_(g.to(torch.bfloat16))
+        if msums is not None:
+            assert n_per_rank * ranks == shape.n_cols and tuple(msums.shape) == (2, ranks)
+            lp_row = t2 - lse2_row[:shape.m_rows].double()[:, None]
+            lp_col = t2 - lse2_col[:shape.n_cols].double()[None, :]
+            for r in range(ranks):
+                cols = slice(r * n_per_rank, (r + 1) * n_per_rank)
+                msums[0, r] = float((w_row * p_row[:, cols] * lp_row[:, cols]).sum())
+                msums[1, r] = float((w_col * p_col[:, cols] * lp_col[:, cols]).sum())
+
+    def gmat_gemm_dot(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out, dot_feat, dot_out):
+        self.gmat_gemm(transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out)
+        if dot_feat is not None:
+            s = float(scale.item())
+            dot_out[0] = float(dot_out[0]) + float((d_out.double() * dot_feat.double()[:, :d_out.shape[1]]).sum() / s)
+
+    def siglip_fwd_e(self, a_rows, b_all, shape, scale, bias, ws, loss, gmat):
+        self.siglip_fwd(a_rows, b_all, shape, scale, bias, ws, loss)
+        self.calls[-1] = "siglip_fwd_e"
+        s = float(scale.item())
+        b = 0.0 if bias is None else float(bias.item())
+        cos = self._cos(a_rows, b_all)
+        g = torch.sigmoid(s * cos + b)
+        idx = torch.arange(shape.m_rows)
+        g[idx, idx + shape.label_offset] -= 1.0
+        self._gview(gmat, shape).copy_(g.to(torch.bfloat16))
+        self.state[("sig", ws.data_ptr())] = (float((g * cos).sum()), float(g.sum()))
+
+    def siglip_e_scalars(self, shape, ws, coef, grad_out, d_scale, d_bias, accumulate):
+        self.calls.append("siglip_e_scalars")
+        gc, gs = self.state.pop(("sig", ws.data_ptr()))
+        go = 1.0 if grad_out is None else float(grad_out.item())
+        if d_scale is not None:
+            d_scale[0] = (float(d_scale[0]) if accumulate else 0.0) + coef * go * gc
+        if d_bias is not None:
+            d_bias[0] = (float(d_bias[0]) if accumulate else 0.0) + coef * go * gs
+
     def siglip_fwd(self, a_rows, b_all, shape, scale, bias, ws, loss):
         self.calls.append("siglip_fwd")
         s = float(scale.item())

@@ -30,7 +30,7 @@ def main():
         case = load_golden(name)
         m = case["meta"]
         assert case["world"] == world, (name, case["world"], world)
-        for backend in ("gmat", "fused"):
+        for backend in ("emat", "gmat", "fused"):
             os.environ["MRCLIP_BWD"] = backend
             n = case["image"].shape[0] // world
             rows = slice(rank * n, (rank + 1) * n)

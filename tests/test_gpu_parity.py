@@ -73,7 +73,7 @@ class EmulatedRanks:
     def clip(self, scale, local_loss, gather_with_grad, grad_output=1.0, backend="fused"):
         eng, dev, W, n, N = self.eng, self.dev, self.W, self.n, self.N
         gmat = None
-        if backend == "gmat":
+        if backend in ("gmat", "emat"):
             gmat = torch.empty(int(eng.gmat_bytes(n, N)) // 2, dtype=torch.bfloat16, device=dev)
         s = torch.tensor([scale], dtype=torch.float32, device=dev)
         go = torch.tensor([grad_output], dtype=torch.float32, device=dev)
@@ -94,6 +94,35 @@ class EmulatedRanks:
         w_oth = 0.0 if (W > 1 and local_loss and not gather_with_grad) else 1.0
         out = []
         ds_all = torch.zeros((W,), dtype=torch.float32, device=dev)
+        if backend == "emat" and w_oth == 1.0:
+            # production order per rank: forward keeps E, the rescale pass turns it into G, two plain GEMMs; the
+            # text gradient is the sum over ranks of the [N, d] partials (NCCL reduce-scatter in production)
+            dt_sum = torch.zeros((N, self.d), dtype=torch.float32, device=dev)
+            msums = torch.zeros((W, 2, W), dtype=torch.float32, device=dev)
+            for r in range(W):
+                rows, sh = self.rows(r), self.shape(r)
+                eng.clip_fwd_tiles_e(self.img_all[rows], self.txt_all, sh, s, 0, N, self.ws, gmat)
+                eng.emat_to_gmat(self.img_all[rows], self.txt_all, sh, lse_row[rows], lse_col, diag[r], s, 1.0, 1.0,
+                                 self.ws, gmat, msums[r], n, W)
+                d_i = torch.empty((n, self.d), dtype=torch.float32, device=dev)
+                part = torch.empty((N, self.d), dtype=torch.float32, device=dev)
+                dot = torch.zeros((1,), dtype=torch.float32, device=dev)
+                eng.gmat_gemm_dot(False, gmat, sh, self.txt_all, coef, s, go, self.ws, d_i, self.img_all[rows], dot)
+                eng.gmat_gemm(True, gmat, sh, self.img_all[rows], coef, s, go, self.ws, part)
+                dt_sum += part
+                out.append(dict(d_image=d_i.cpu().numpy(), dot=float(dot)))
+            # scale * dL_r/dscale = L_r + ln2/(2n) * (negative entropies of my rows + of my columns)
+            ds_r = [grad_output / scale * (float(losses[r]) + 0.6931471805599453 * 0.5 / n *
+                                           float(msums[r, 0].sum() + msums[:, 1, r].sum())) for r in range(W)]
+            for r in range(W):
+                out[r]["d_text"] = dt_sum[self.rows(r)].cpu().numpy()
+                out[r]["loss"] = float(losses.mean() if global_mode else losses[r])
+                out[r]["d_scale"] = float(np.mean(ds_r)) if global_mode else ds_r[r]
+                if W == 1:   # the GEMM's <dI, I> / scale must tell the same story (bf16 noise of G: large blocks only)
+                    assert abs(out[r]["dot"] - ds_r[r]) <= 2e-2 * abs(ds_r[r]) + 1e-5 or n * N < (1 << 22)
+            return out
+        if backend == "emat":
+            backend = "gmat"     # (local_loss, no gather_with_grad): the two gradients need different G blocks
         for r in range(W):
             d_i = torch.empty((n, self.d), dtype=torch.float32, device=dev)
             d_t = torch.empty((n, self.d), dtype=torch.float32, device=dev)
@@ -124,12 +153,30 @@ class EmulatedRanks:
     def siglip(self, scale, bias, grad_output=1.0, backend="fused"):
         eng, dev, W, n, N = self.eng, self.dev, self.W, self.n, self.N
         gmat = None
-        if backend == "gmat":
+        if backend in ("gmat", "emat"):
             gmat = torch.empty(int(eng.gmat_bytes(n, N)) // 2, dtype=torch.bfloat16, device=dev)
         s = torch.tensor([scale], dtype=torch.float32, device=dev)
         b = torch.tensor([bias], dtype=torch.float32, device=dev)
         go = torch.tensor([grad_output], dtype=torch.float32, device=dev)
         out = []
+        if backend == "emat":
+            dt_sum = torch.zeros((N, self.d), dtype=torch.float32, device=dev)
+            for r in range(W):
+                rows, sh = self.rows(r), self.shape(r)
+                loss = torch.zeros((1,), dtype=torch.float32, device=dev)
+                ds = torch.zeros((1,), dtype=torch.float32, device=dev)
+                db = torch.zeros((1,), dtype=torch.float32, device=dev)
+                d_i = torch.empty((n, self.d), dtype=torch.float32, device=dev)
+                part = torch.empty((N, self.d), dtype=torch.float32, device=dev)
+                eng.siglip_fwd_e(self.img_all[rows], self.txt_all, sh, s, b, self.ws, loss, gmat)
+                eng.siglip_e_scalars(sh, self.ws, 1.0 / n, go, ds, db, False)
+                eng.gmat_gemm(False, gmat, sh, self.txt_all, 1.0 / n, s, go, self.ws, d_i)
+                eng.gmat_gemm(True, gmat, sh, self.img_all[rows], 1.0 / n, s, go, self.ws, part)
+                dt_sum += part
+                out.append(dict(loss=float(loss), d_image=d_i.cpu().numpy(), d_scale=float(ds), d_bias=float(db)))
+            for r in range(W):
+                out[r]["d_text"] = dt_sum[self.rows(r)].cpu().numpy()
+            return out
         for r in range(W):
             loss = torch.zeros((1,), dtype=torch.float32, device=dev)
             ds = torch.zeros((1,), dtype=torch.float32, device=dev)
@@ -167,7 +214,7 @@ def _check_rank(out, ref, kind):
         assert abs(out["d_bias"] - float(ref["d_bias"])) <= GRAD_TOL * abs(float(ref["d_bias"])) + 1e-7
 
 
-@pytest.mark.parametrize("backend", ["gmat", "fused"])
+@pytest.mark.parametrize("backend", ["emat", "gmat", "fused"])
 @pytest.mark.parametrize("name", golden_names())
 def test_kernels_match_reference_golden(name, backend):
     """Every fixture recorded from the reference, all ranks emulated on one GPU through the C ABI,
@@ -229,7 +276,7 @@ def test_module_accepts_amp_dtypes(dtype):
     assert rel_err(t.grad.float().cpu().numpy(), ref["d_text"]) <= GRAD_TOL
 
 
-@pytest.mark.parametrize("backend", ["gmat", "fused"])
+@pytest.mark.parametrize("backend", ["emat", "gmat", "fused"])
 @pytest.mark.parametrize("N,D,W,scale,mode", [
     (1024, 768, 1, 14.285714, (False, False)),
     (1536, 512, 4, 100.0, (True, True)),
@@ -251,7 +298,7 @@ def test_clip_vs_oracle(N, D, W, scale, mode, backend):
         assert abs(out[r]["d_scale"] - ref[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref[r]["d_logit_scale"]) + 1e-6
 
 
-@pytest.mark.parametrize("backend", ["gmat", "fused"])
+@pytest.mark.parametrize("backend", ["emat", "gmat", "fused"])
 @pytest.mark.parametrize("N,D,W", [(1024, 768, 2), (520, 264, 1), (96, 24, 3)])
 def test_siglip_vs_oracle(N, D, W, backend):
     from oracle.clip_oracle import siglip_loss_oracle
@@ -286,7 +333,8 @@ def _torch_fp32_clip(img, txt, scale):
         torch.backends.cuda.matmul.allow_tf32 = old
 
 
-@pytest.mark.parametrize("N,D,backend", [(8192, 512, "gmat"), (8192, 512, "fused"), (32768, 768, "gmat")])
+@pytest.mark.parametrize("N,D,backend", [(8192, 512, "emat"), (8192, 512, "gmat"), (8192, 512, "fused"),
+                                         (32768, 768, "emat")])
 def test_full_size_vs_torch_fp32_and_properties(N, D, backend, monkeypatch):
     """BASELINE sizes (config 3 at world_size 1 is N=32768, D=768): fp32 torch on the same GPU as the
     checker, plus properties that need no checker at all."""
@@ -360,3 +408,48 @@ def test_gradscaler_grad_output_and_workspace_reuse():
     assert abs(s1.grad.item() / 65536.0 - s.grad.item()) <= 1e-5 * abs(s.grad.item())
     with torch.no_grad():
         assert abs(mod(img.to(dev), txt.to(dev), 14.285714).item() - l0.item()) <= 1e-6 * abs(l0.item())
+
+
+def test_emat_guard_falls_back_to_exact_recompute(monkeypatch):
+    """A row that dominates its 32 x 64 sub-tile by > 2^80 makes bf16 E of its neighbours flush to zero; the device
+    guard must notice, the exact recompute must rewrite the block, and the result must still match the oracle."""
+    from mrclip_b200 import ClipLoss
+    from mrclip_b200.engine import default_engine
+    monkeypatch.setenv("MRCLIP_BWD", "emat")
+    dev = torch.device("cuda:0")
+    N, D, scale = 256, 64, 100.0
+    img, txt = _features(N, D, 5, corr=0.0)
+    img[0] = 0.0
+    img[0, 0] = 1.0
+    txt[0] = img[0]                 # S_00 = 100 (144 in log2 units); every other logit of the band is ~ +-15
+    mod = ClipLoss()
+    i = img.to(dev).requires_grad_(True)
+    t = txt.to(dev).requires_grad_(True)
+    s = torch.tensor(scale, device=dev, requires_grad=True)
+    loss = mod(i, t, s)
+    loss.backward()
+    ws = next(w for lst in mod._pool._free.values() for w in lst)
+    eng = default_engine()
+    from mrclip_b200._cabi import Shape
+    off = eng.lib.mrclip_emat_flag(Shape(N, N, D, 0), ws.scratch.data_ptr()) - ws.scratch.data_ptr()
+    assert int(ws.scratch[off:off + 4].view(torch.int32).item()) == 1, "guard flag not raised"
+    from oracle.clip_oracle import clip_loss_oracle
+    ref = clip_loss_oracle([img.numpy()], [txt.numpy()], scale)[0]
+    assert abs(loss.item() - ref["loss"]) <= LOSS_TOL * abs(ref["loss"])
+    assert rel_err(i.grad.cpu().numpy(), ref["d_image"]) <= GRAD_TOL
+    assert rel_err(t.grad.cpu().numpy(), ref["d_text"]) <= GRAD_TOL
+    assert abs(s.grad.item() - ref["d_logit_scale"]) <= GRAD_TOL * abs(ref["d_logit_scale"]) + 1e-7
+    # two ranks, local loss: the per-rank d_scale then comes from the recompute's per-chunk partials
+    N2 = 1024
+    img2, txt2 = _features(N2, D, 6, corr=0.0)
+    img2[0] = 0.0
+    img2[0, 0] = 1.0
+    txt2[0] = img2[0]
+    out = EmulatedRanks(img2, txt2, 2).clip(scale, True, True, backend="emat")
+    ref2 = clip_loss_oracle([img2[:512].numpy(), img2[512:].numpy()], [txt2[:512].numpy(), txt2[512:].numpy()], scale,
+                            True, True)
+    for r in range(2):
+        assert abs(out[r]["loss"] - ref2[r]["loss"]) <= LOSS_TOL * abs(ref2[r]["loss"]) + 1e-6
+        assert rel_err(out[r]["d_image"], ref2[r]["d_image"]) <= GRAD_TOL
+        assert rel_err(out[r]["d_text"], ref2[r]["d_text"]) <= GRAD_TOL
+        assert abs(out[r]["d_scale"] - ref2[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref2[r]["d_logit_scale"]) + 1e-6
