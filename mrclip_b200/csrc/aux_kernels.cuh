@@ -115,26 +115,38 @@ __global__ void reduce_rows_kernel(const float2* __restrict__ row_part, int slot
 }
 
 // per-column merge over the 32-row bands -> (max2, sum) of this rank's rows.
-// block = 32 columns x 32 band slices (1024 threads); slices are merged through shared memory.
-__global__ void reduce_cols_kernel(const float* __restrict__ col_l, const float* __restrict__ col_c,
-                                   int bands, int n_cols, int n_pad, float* __restrict__ out_m,
-                                   float* __restrict__ out_l) {
-  __shared__ float sm[32][33], sl[32][33];
-  const int c = threadIdx.x, slice = threadIdx.y;
-  const int j = blockIdx.x * 32 + c;
-  float m = -CUDART_INF_F, l = 0.f;
-  if (j < n_cols) {
-    for (int b = slice; b < bands; b += 32) {
-      const float ref = col_c[(size_t)b * (n_pad / 64) + j / 64];
-      const float v = col_l[(size_t)b * n_pad + j];
-      lse2_merge(m, l, ref, v);
-    }
+// The forward references all 64 columns of a (band, column-block) sub-tile to one value c (col_c), so a block
+// that owns one column block first finds g = max_band c and the weights 2^(c - g) (one exp2 per band, in shared
+// memory) and then only streams col_l with one FMA per element: 64 columns x 16 band slices per block.
+__global__ void __launch_bounds__(1024)
+reduce_cols_kernel(const float* __restrict__ col_l, const float* __restrict__ col_c, int bands, int n_cols,
+                   int n_pad, float* __restrict__ out_m, float* __restrict__ out_l) {
+  extern __shared__ float wgt[];          // [bands]
+  __shared__ float red[32];
+  __shared__ float part[16][64];
+  const int cb = blockIdx.x, ncb = n_pad / 64;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float m = -CUDART_INF_F;
+  for (int b = tid; b < bands; b += 1024) {
+    const float c = col_c[(size_t)b * ncb + cb];
+    wgt[b] = c;
+    m = fmaxf(m, c);
   }
-  sm[slice][c] = m;
-  sl[slice][c] = l;
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = red[0];
+  for (int w = 1; w < 32; ++w) m = fmaxf(m, red[w]);
+  for (int b = tid; b < bands; b += 1024) wgt[b] = exp2f(wgt[b] - m);   // m is finite: dead sub-tiles store c = 0
+  __syncthreads();
+  const int c = tid & 63, slice = tid >> 6;
+  const int j = cb * 64 + c;
+  float l = 0.f;
+  for (int b = slice; b < bands; b += 16) l = fmaf(col_l[(size_t)b * n_pad + j], wgt[b], l);
+  part[slice][c] = l;
   __syncthreads();
   if (slice == 0 && j < n_cols) {
-    for (int k = 1; k < 32; ++k) lse2_merge(m, l, sm[k][c], sl[k][c]);
+    for (int k = 1; k < 16; ++k) l += part[k][c];
     out_m[j] = m;
     out_l[j] = l;
   }
@@ -318,7 +330,7 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
   if (skip_if != nullptr && __ldg(skip_if) != 0) return;
   __shared__ __align__(16) float cfac[1024];
   __shared__ __align__(16) float lcol[WSUM ? 1024 : 4];
-  __shared__ float bacc[4][2];
+  __shared__ float bacc[2][64];   // per-block sums by column owner (ranks <= 64)
   const int band = blockIdx.y;
   const int col0 = blockIdx.x * 1024;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -331,18 +343,23 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
       f = w_col * ex2f(fminf(__ldg(cw_row + (j >> 6)) - lc, 120.f));
     }
     cfac[c] = f;
-    if (WSUM) lcol[c] = lc;
+    // WSUM: w_col * Pcol * log2 Pcol = e * cfac * (log2 e + c - lc) = cfac * (e log2 e) + dfac * e
+    if (WSUM) lcol[c] = (f > 0.f) ? f * (__ldg(cw_row + (min(j, n_pad - 1) >> 6)) - lc) : 0.f;
   }
-  if (WSUM && tid < 8) bacc[tid >> 1][tid & 1] = 0.f;
+  if (WSUM && tid < 128) bacc[tid >> 6][tid & 63] = 0.f;
   __syncthreads();
   const float wsum = w_row + w_col;
-  float accr[4] = {0.f, 0.f, 0.f, 0.f}, accc[4] = {0.f, 0.f, 0.f, 0.f};
-  bool strad[4] = {false, false, false, false};   // this thread's 8 columns of segment s straddle two ranks
-  if (WSUM && n_per_rank % 8 != 0) {
+  // WSUM: this thread's 8 columns of segment s belong to rank r0[s] up to (excluding) element ks[s], to rank
+  // r0[s] + 1 from there on (n_per_rank >= 8, so at most one boundary falls into a group)
+  float acc_lo_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_lo_c[4] = {0.f, 0.f, 0.f, 0.f};
+  float acc_hi_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_hi_c[4] = {0.f, 0.f, 0.f, 0.f};
+  int r0[4] = {0, 0, 0, 0}, ks[4] = {8, 8, 8, 8};
+  if (WSUM) {
 #pragma unroll
     for (int seg = 0; seg < 4; ++seg) {
       const int j = col0 + seg * 256 + lane * 8;
-      strad[seg] = (j / n_per_rank) != ((j + 7) / n_per_rank);
+      r0[seg] = j / n_per_rank;
+      ks[seg] = min(8, (r0[seg] + 1) * n_per_rank - j);
     }
   }
 #pragma unroll 1
@@ -355,7 +372,7 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
     for (int seg = 0; seg < 4; ++seg) {
       const int c = seg * 256 + lane * 8;
       const int j = col0 + c;
-      if (j >= n_pad) continue;
+      if (j < n_pad) {
       uint4 v = *reinterpret_cast<const uint4*>(row + j);
       const float cw = __ldg(cw_row + (j >> 6));
       const float rf = w_row * ex2f(fminf(cw - lr, 120.f));
@@ -369,52 +386,48 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
         e[2 * k] = __uint_as_float(w[k] << 16);
         e[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = e[k] * (rf + cf[k]);
+      // the positive of row i (at most one per thread-row): exact probabilities from diag2 replace the entry
       const bool diag_here = (jd >= j && jd < j + 8 && i < m_rows);
-      float dg = 0.f;
+      const int kd = diag_here ? jd - j : -1;
+      float gd = 0.f, trd = 0.f, tcd = 0.f;
       if (diag_here) {
-        dg = __ldg(diag2 + i);
-        const float gd = w_row * ex2f(dg - lr) + w_col * ex2f(dg - __ldg(lse2_col + jd)) - wsum;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k == jd - j) g[k] = gd;
+        const float dg = __ldg(diag2 + i);
+        const float lpr = dg - lr, lpc = dg - __ldg(lse2_col + jd);
+        const float pr = w_row * ex2f(lpr), pc = w_col * ex2f(lpc);
+        gd = pr + pc - wsum;
+        trd = pr * lpr;
+        tcd = pc * lpc;
       }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = (k == kd) ? gd : e[k] * (rf + cf[k]);
       if (WSUM) {
         const float4 l0 = *reinterpret_cast<const float4*>(lcol + c);
         const float4 l1 = *reinterpret_cast<const float4*>(lcol + c + 4);
-        const float lc[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        float tr[8], tc[8];   // w * P * log2 P per element, both directions (0 for flushed / padded entries)
+        const float df[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+        // w * P * log2 P per element, both directions, with t = e log2 e (0 for flushed / padded entries):
+        //   row: rf * (t + e * (c - lr))        col: cfac * t + dfac * e
+        const float dr = (rf > 0.f) ? cw - lr : 0.f;
+        float tr[8], tc[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const float s2 = cw + lg2f(e[k]);
-          const bool live = e[k] > 0.f;
-          tr[k] = live ? e[k] * rf * (s2 - lr) : 0.f;
-          tc[k] = live ? e[k] * cf[k] * (s2 - lc[k]) : 0.f;
+          const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
+          tr[k] = (k == kd) ? trd : rf * fmaf(e[k], dr, t);
+          tc[k] = (k == kd) ? tcd : fmaf(cf[k], t, df[k] * e[k]);
         }
-        if (diag_here) {   // the positive: exact probabilities from diag2
-          const float lpr = dg - lr, lpc = dg - __ldg(lse2_col + jd);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (k == jd - j) {
-              tr[k] = w_row * ex2f(lpr) * lpr;
-              tc[k] = w_col * ex2f(lpc) * lpc;
-            }
-        }
-        if (!strad[seg]) {
+        if (ks[seg] == 8) {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            accr[seg] += tr[k];
-            accc[seg] += tc[k];
+            acc_lo_r[seg] += tr[k];
+            acc_lo_c[seg] += tc[k];
           }
-        } else {   // the 8 columns straddle two ranks (n not a multiple of 8): attribute element-wise, rarely taken
+        } else {
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            if (j + k < n_per_rank * ranks) {
-              const int r = (j + k) / n_per_rank;
-              atomicAdd(msums + r, tr[k]);
-              atomicAdd(msums + ranks + r, tc[k]);
-            }
+            const bool lo = k < ks[seg];
+            acc_lo_r[seg] += lo ? tr[k] : 0.f;
+            acc_lo_c[seg] += lo ? tc[k] : 0.f;
+            acc_hi_r[seg] += lo ? 0.f : tr[k];
+            acc_hi_c[seg] += lo ? 0.f : tc[k];
           }
         }
       }
@@ -423,38 +436,37 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
       v.z = pack_bf16x2(g[4], g[5]);
       v.w = pack_bf16x2(g[6], g[7]);
       *reinterpret_cast<uint4*>(row + j) = v;
+      }
     }
   }
   if (WSUM) {
+    const int n_all = n_per_rank * ranks;
 #pragma unroll
     for (int seg = 0; seg < 4; ++seg) {
-      const int j_lo = col0 + seg * 256, j_hi = j_lo + 255;
-      const int n_all = n_per_rank * ranks;
-      if (j_lo >= n_all) continue;
-      const int r_lo = j_lo / n_per_rank, r_hi = min(j_hi, n_all - 1) / n_per_rank;
-      if (r_lo == r_hi) {   // the whole 256-column segment belongs to one rank (block-uniform)
-        const float tr = warp_sum(accr[seg]), tc = warp_sum(accc[seg]);
+      const int j_lo = col0 + seg * 256;
+      if (j_lo < n_all) {
+      const int r_lo = j_lo / n_per_rank, r_hi = min(j_lo + 255, n_all - 1) / n_per_rank;
+      if (r_lo == r_hi) {   // the whole 256-column segment belongs to one rank (block-uniform test)
+        const float tr = warp_sum(acc_lo_r[seg]), tc = warp_sum(acc_lo_c[seg]);
         if (lane == 0) {
-          atomicAdd(&bacc[seg][0], tr);
-          atomicAdd(&bacc[seg][1], tc);
+          atomicAdd(&bacc[0][r_lo], tr);
+          atomicAdd(&bacc[1][r_lo], tc);
         }
-      } else {
-        const int j = j_lo + lane * 8;
-        if (j < n_all) {
-          const int r = min(j / n_per_rank, ranks - 1);
-          atomicAdd(msums + r, accr[seg]);
-          atomicAdd(msums + ranks + r, accc[seg]);
+      } else if (col0 + seg * 256 + lane * 8 < n_all) {   // a rank boundary inside the segment: lane by lane
+        atomicAdd(&bacc[0][r0[seg]], acc_lo_r[seg]);
+        atomicAdd(&bacc[1][r0[seg]], acc_lo_c[seg]);
+        if (ks[seg] < 8 && r0[seg] + 1 < ranks) {
+          atomicAdd(&bacc[0][r0[seg] + 1], acc_hi_r[seg]);
+          atomicAdd(&bacc[1][r0[seg] + 1], acc_hi_c[seg]);
         }
+      }
       }
     }
     __syncthreads();
-    if (tid < 8) {
-      const int seg = tid >> 1, which = tid & 1;
-      const int j_lo = col0 + seg * 256, n_all = n_per_rank * ranks;
-      if (j_lo < n_all) {
-        const int r_lo = j_lo / n_per_rank, r_hi = min(j_lo + 255, n_all - 1) / n_per_rank;
-        if (r_lo == r_hi) atomicAdd(msums + which * ranks + r_lo, bacc[seg][which]);
-      }
+    if (tid < 2 * ranks) {
+      const int which = tid / ranks, r = tid - which * ranks;
+      const float v = bacc[which][r];
+      if (v != 0.f) atomicAdd(msums + which * ranks + r, v);
     }
   }
 }

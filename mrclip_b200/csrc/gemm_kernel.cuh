@@ -13,6 +13,7 @@
 //
 // Replaces the autograd matmul-backward GEMMs of loss.py:117-124.
 #pragma once
+#include "aux_kernels.cuh"
 #include "ptx.cuh"
 #include "tile_kernel.cuh"
 
@@ -34,6 +35,13 @@ struct GemmParams {
   int num_items;
   int m_pad, d_pad;
   float* dpart;      // [ksplit][m_pad][d_pad]
+  // ksplit == 1: the epilogue scales and stores the result itself (no partials, no grad_reduce pass)
+  void* out;         // [m_rows][out_ld] of out_dtype (0 f32, 1 bf16, 2 f16), NULL -> write dpart
+  long out_ld;
+  int out_dtype, d_valid;
+  float coef;
+  const float* scale;
+  const float* grad_out;   // may be NULL
 };
 
 // MN-major (M contiguous) A operand tile: K rows of 128 bytes (64 M-elements), 128B swizzle.
@@ -189,12 +197,41 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const int grow = rb * kBM + row_in_tile;
       float* out_row = p.dpart + ((size_t)ks * p.m_pad + grow) * p.d_pad + dt * kGemmBN;
+      float mul = 1.f;
+      if (p.out != nullptr) {
+        mul = p.coef * __ldg(p.scale);
+        if (p.grad_out != nullptr) mul *= __ldg(p.grad_out);
+      }
 #pragma unroll 1
       for (int c0 = h * 128; c0 < (int)(h + 1) * 128; c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0, r);
         tmem_ld_wait();
-        if (grow < p.m_rows) {
+        if (p.out != nullptr) {
+          // direct epilogue: scale, cast, store (row-wise 16/32-byte pieces; the tile's columns may be ragged)
+          if (grow < p.m_rows) {
+            const int col = dt * kGemmBN + c0;
+            if (p.out_dtype == DT_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col;
+              if (col + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(o + 4 * j) =
+                      make_float4(__uint_as_float(r[4 * j]) * mul, __uint_as_float(r[4 * j + 1]) * mul,
+                                  __uint_as_float(r[4 * j + 2]) * mul, __uint_as_float(r[4 * j + 3]) * mul);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < p.d_valid) o[j] = __uint_as_float(r[j]) * mul;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.d_valid)
+                  store_from_float(p.out, p.out_dtype, (size_t)grow * p.out_ld + col + j, __uint_as_float(r[j]) * mul);
+            }
+          }
+        } else if (grow < p.m_rows) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float4 o;

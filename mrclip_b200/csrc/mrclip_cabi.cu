@@ -160,7 +160,15 @@ GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
   const int base = g.num_rb * g.num_dt;
   int best = 1;
   double best_eff = 0.0;
-  for (int ks = 1; ks <= 16; ++ks) {
+  // short contractions with many output tiles (the [N, d] text-gradient partial of one rank, K = n): the fp32
+  // split-K partials would cost more HBM traffic than the wave quantisation they repair -> one split, and the
+  // GEMM's epilogue scales and stores the result itself
+  int max_ks = (g.num_kb <= 128 && base >= 3 * sms) ? 1 : 16;
+  if (const char* e = getenv("MRCLIP_GEMM_MAX_KSPLIT")) {   // test / experiment knob
+    const int v = atoi(e);
+    if (v >= 1 && v <= 16) max_ks = v;
+  }
+  for (int ks = 1; ks <= max_ks; ++ks) {
     const int per = ceil_div(g.num_kb, ks);
     if (ks > 1 && per < 16) break;
     const int ks_eff = ceil_div(g.num_kb, per);
@@ -461,7 +469,18 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
   p.m_pad = g.m_pad;
   p.d_pad = g.d_pad;
   p.dpart = reinterpret_cast<float*>(ws);
+  const bool direct = (g.ksplit == 1 && xf.dot_feat == nullptr);
+  if (direct) {
+    p.out = d_out;
+    p.out_ld = out_ld;
+    p.out_dtype = out_dtype;
+    p.d_valid = d;
+    p.coef = coef;
+    p.scale = scale;
+    p.grad_out = grad_out;
+  }
   if (int e = transposed ? launch_gemm<true>(ma, mb, p, st) : launch_gemm<false>(ma, mb, p, st)) return e;
+  if (direct) return 0;
   const long total = (long)out_rows * (g.d_pad / 4);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
@@ -566,9 +585,18 @@ int mrclip_clip_fwd_reduce(mrclip_shape sh, void* ws, float* lse2_row, float* co
   uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
   reduce_rows_kernel<<<ceil_div(sh.m_rows, 256), 256, 0, st>>>(
       reinterpret_cast<const float2*>(wsb + w.row_part), f.total_chunks * 2, sh.m_rows, f.m_pad, lse2_row);
-  reduce_cols_kernel<<<ceil_div(sh.n_cols, 32), dim3(32, 32), 0, st>>>(
-      reinterpret_cast<const float*>(wsb + w.col_l), reinterpret_cast<const float*>(wsb + w.col_c),
-      ceil_div(sh.m_rows, 32), sh.n_cols, f.n_pad, col_m, col_l);
+  {
+    const int bands = ceil_div(sh.m_rows, 32);
+    static bool attr_set = false;
+    if (!attr_set && bands * sizeof(float) > 48 * 1024) {
+      CUDA_TRY(cudaFuncSetAttribute(reduce_cols_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    if (bands * sizeof(float) > 200 * 1024) return fail(-1, "m_rows=%d too large for the column reduce", sh.m_rows);
+    reduce_cols_kernel<<<ceil_div(sh.n_cols, 64), 1024, bands * sizeof(float), st>>>(
+        reinterpret_cast<const float*>(wsb + w.col_l), reinterpret_cast<const float*>(wsb + w.col_c), bands,
+        sh.n_cols, f.n_pad, col_m, col_l);
+  }
   g_launches.fetch_add(2);
   CUDA_TRY(cudaGetLastError());
   CUDA_TRY(cudaMemcpyAsync(diag2, wsb + w.diag2, (size_t)sh.m_rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -707,6 +735,8 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
   if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
   if (!emat || !lse2_row || !lse2_col || !diag2) return fail(-1, "emat_transform: NULL argument");
   if (msums && skip_if && !scale) return fail(-1, "emat_transform: scale is needed for the fallback sums");
+  if (msums && (ranks > 64 || (ranks > 1 && n_per_rank < 8)))
+    return fail(-1, "emat_transform: split sums need ranks <= 64 and n_per_rank >= 8 (got %d x %d)", ranks, n_per_rank);
   if (msums && (n_per_rank <= 0 || ranks <= 0 || (long)n_per_rank * ranks != sh.n_cols))
     return fail(-1, "emat_transform: n_per_rank * ranks must equal n_cols");
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);

@@ -210,8 +210,10 @@ def _check_inputs(image_features, text_features):
         raise ValueError("empty batch")
 
 
-def _gather_packed(eng, ws, image_features, text_features, rank, world):
-    """Pack the local features to bf16 straight into their slot and all-gather in place."""
+def _gather_packed(eng, ws, image_features, text_features, rank, world, gather_images=True):
+    """Pack the local features to bf16 straight into their slot and all-gather in place.  The emat backend
+    never touches another rank's image rows (dI_r = G_r . T_all, dT partial = G_r^T . I_r), so it gathers
+    the text side only."""
     n = ws.n
     rows = slice(rank * n, (rank + 1) * n)
     img = image_features.detach()
@@ -223,7 +225,8 @@ def _gather_packed(eng, ws, image_features, text_features, rank, world):
     eng.pack(img, ws.img_all[rows])
     eng.pack(txt, ws.txt_all[rows])
     if world > 1:
-        _all_gather_rows(ws.img_all, rows)
+        if gather_images:
+            _all_gather_rows(ws.img_all, rows)
         _all_gather_rows(ws.txt_all, rows)
 
 
@@ -256,10 +259,13 @@ class _ClipLossFn(torch.autograd.Function):
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
 
-        _gather_packed(eng, ws, image_features, text_features, rank, world)
         # (local_loss, not gather_with_grad) gives the two gradients different G matrices; it keeps the gmat path
         split_g = world > 1 and module.local_loss and not module.gather_with_grad
-        if any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g:
+        split_g = split_g or (world > 1 and (n < 8 or world > 64))   # limits of the per-owner entropy sums
+        use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g
+        _gather_packed(eng, ws, image_features, text_features, rank, world,
+                       gather_images=not use_emat and any(ctx.needs_input_grad))
+        if use_emat:
             eng.clip_fwd_tiles_e(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
             ws.has_emat = True
         else:
@@ -450,9 +456,11 @@ class _SigLipLossFn(torch.autograd.Function):
         bias = _scalar_f32(logit_bias, device) if logit_bias is not None else None
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
-        _gather_packed(eng, ws, image_features, text_features, rank, world)
+        use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat"
+        _gather_packed(eng, ws, image_features, text_features, rank, world,
+                       gather_images=not use_emat and any(ctx.needs_input_grad))
         loss = torch.empty((1,), dtype=torch.float32, device=device)
-        if any(ctx.needs_input_grad) and _backend(eng, ws) == "emat":
+        if use_emat:
             # no normaliser: the forward can store G = sigmoid(z) - delta itself
             eng.siglip_fwd_e(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss, ws.gmat_buffer(eng))
             ws.has_emat = True

@@ -453,3 +453,21 @@ def test_emat_guard_falls_back_to_exact_recompute(monkeypatch):
         assert rel_err(out[r]["d_image"], ref2[r]["d_image"]) <= GRAD_TOL
         assert rel_err(out[r]["d_text"], ref2[r]["d_text"]) <= GRAD_TOL
         assert abs(out[r]["d_scale"] - ref2[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref2[r]["d_logit_scale"]) + 1e-6
+
+
+@pytest.mark.parametrize("N,D,W", [(1000, 200, 1), (1536, 512, 4)])
+def test_gemm_direct_epilogue(N, D, W, monkeypatch):
+    """single-split GEMMs scale and store their result themselves (no fp32 partials, no reduce pass); forced here
+    at small sizes, where the planner would normally split K"""
+    from oracle.clip_oracle import clip_loss_oracle
+    monkeypatch.setenv("MRCLIP_GEMM_MAX_KSPLIT", "1")
+    img, txt = _features(N, D, 4000 + N, corr=0.2)
+    n = N // W
+    parts = lambda x: [x[r * n:(r + 1) * n].numpy() for r in range(W)]
+    ref = clip_loss_oracle(parts(img), parts(txt), 14.285714, True, True)
+    for backend in ("emat", "gmat"):
+        out = EmulatedRanks(img, txt, W).clip(14.285714, True, True, backend=backend)
+        for r in range(W):
+            assert rel_err(out[r]["d_image"], ref[r]["d_image"]) <= GRAD_TOL
+            assert rel_err(out[r]["d_text"], ref[r]["d_text"]) <= GRAD_TOL
+            assert abs(out[r]["d_scale"] - ref[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref[r]["d_logit_scale"]) + 1e-6
