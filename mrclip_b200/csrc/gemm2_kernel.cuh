@@ -1,0 +1,224 @@
+// Gradient contraction on CTA pairs: the gemm_kernel of gemm_kernel.cuh with tcgen05 cta_group::2.
+//
+// Two CTAs of a cluster (the two SMs of a TPC) own one 256 x 256 output tile: CTA c holds rows c*128.. of A and
+// of the accumulator (its own TMEM) and loads only HALF of the B tile (N columns c*128..); the tensor cores of
+// both SMs read both halves.  Per 64-wide K block a CTA therefore pulls 16 KB (A) + 16 KB (half B) through L2
+// instead of 16 + 32 KB: operand delivery was what bounded the single-CTA kernel, and the
+// smaller stage lets the TMA ring hold 6 K blocks instead of 4.
+//
+// Protocol (one MMA issuer for the pair, in the leader CTA = cluster rank 0):
+//   * both producers load into their own shared memory but credit the bytes to the LEADER's full barrier
+//     (cp.async.bulk.tensor ... .cta_group::2, barrier address mapped with mapa);
+//   * tcgen05.commit multicasts the "stage free" / "accumulator ready" arrivals to the barriers of both CTAs;
+//   * both epilogues drain their own TMEM half and arrive on the leader's "accumulator free" barrier.
+#pragma once
+#include "gemm_kernel.cuh"
+
+namespace mrclip {
+
+constexpr int kG2StageBytes = 16384 + 16384;
+constexpr int kG2Stages = 6;
+constexpr int kG2Bars = 2 * kG2Stages + 4;
+constexpr int kG2SmemBytes = kG2Stages * kG2StageBytes + kG2Bars * 8 + 16 + 1024;
+
+// GemmParams::num_rb counts 256-row pair blocks here.
+template <bool A_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const GemmParams p) {
+  constexpr int STAGES = kG2Stages;
+  // M = 256 across the pair; bit 15 = A is MN-major, bit 16 = B is MN-major
+  constexpr uint32_t IDESC = make_idesc_bf16(2 * kBM, kGemmBN) | (A_MN ? (1u << 15) : 0u) | (1u << 16);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const uint32_t stage_base = smem_u32(smem);
+  uint8_t* bar_ptr = smem + STAGES * kG2StageBytes;
+  const uint32_t bar_base = smem_u32(bar_ptr);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kG2Bars * 8);
+  auto bar_full = [&](int s) { return bar_base + 8u * s; };
+  auto bar_empty = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto bar_accfull = [&](int b) { return bar_base + 8u * (2 * STAGES + b); };
+  auto bar_accempty = [&](int b) { return bar_base + 8u * (2 * STAGES + 2 + b); };
+
+  const uint32_t warp = threadIdx.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t cta = cluster_ctarank();          // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(bar_full(s), 1);
+        mbar_init(bar_empty(s), 1);
+      }
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(bar_accfull(b), 1);
+        mbar_init(bar_accempty(b), 2 * kEpiWarps);   // the epilogue warps of both CTAs
+      }
+      mbar_init_fence();
+    }
+    __syncwarp();
+    tmem_alloc_pair(smem_u32(tmem_slot), 512);
+    tmem_relinquish_pair();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // the peer's barriers exist before anything is credited to them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto decode = [&](int item, int& rb, int& dt, int& ks, int& kb0, int& kb1) {
+    dt = item % p.num_dt;   // dt fastest: the pairs that share one A block run side by side (L2 reuse of G)
+    int rest = item / p.num_dt;
+    rb = rest % p.num_rb;
+    ks = rest / p.num_rb;
+    kb0 = ks * p.kb_per_split;
+    kb1 = min(kb0 + p.kb_per_split, p.num_kb);
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    uint32_t stage = 0, phase = 0;
+    for (int item = pair; item < p.num_items; item += num_pairs) {
+      int rb, dt, ks, kb0, kb1;
+      decode(item, rb, dt, ks, kb0, kb1);
+      const int row0 = rb * 2 * kBM + (int)cta * kBM;          // this CTA's 128 rows of the pair tile
+      const int col0 = dt * kGemmBN + (int)cta * (kGemmBN / 2);  // this CTA's half of the B tile
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(bar_empty(stage), phase ^ 1);
+        if (elect_one()) {
+          const uint32_t full_leader = mapa_shared(bar_full(stage), 0);
+          if (cta == 0) mbar_expect_tx(bar_full(stage), 2 * kG2StageBytes);   // bytes of both CTAs
+          const uint32_t dst = stage_base + stage * kG2StageBytes;
+          if (A_MN) {
+            tma_load_2d_pair(dst, &tmA, full_leader, row0, kb * kBK);
+            tma_load_2d_pair(dst + 8192, &tmA, full_leader, row0 + 64, kb * kBK);
+          } else {
+            tma_load_2d_pair(dst, &tmA, full_leader, kb * kBK, row0);
+          }
+          tma_load_2d_pair(dst + 16384, &tmB, full_leader, col0, kb * kBK);
+          tma_load_2d_pair(dst + 16384 + 8192, &tmB, full_leader, col0 + 64, kb * kBK);
+        }
+        __syncwarp();
+        if (++stage == STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (cta == 0) {
+      uint32_t stage = 0, phase = 0, acc_use = 0;
+      for (int item = pair; item < p.num_items; item += num_pairs) {
+        int rb, dt, ks, kb0, kb1;
+        decode(item, rb, dt, ks, kb0, kb1);
+        const uint32_t buf = acc_use & 1, use = acc_use >> 1;
+        mbar_wait(bar_accempty(buf), (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + buf * kGemmBN;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(bar_full(stage), phase);
+          tc_fence_after();
+          const uint32_t a = stage_base + stage * kG2StageBytes;
+          const uint64_t bdesc = make_mnmajor_sw128_desc(a + 16384, 8192);
+          const uint64_t adesc = A_MN ? make_mnmajor_sw128_desc(a, 8192) : make_kmajor_sw128_desc(a);
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < kBK / 16; ++k)
+              umma_bf16_pair(d_tmem, adesc + (A_MN ? 128 * k : 2 * k), bdesc + 128 * k, IDESC,
+                             (kb > kb0 || k > 0) ? 1u : 0u);
+            umma_commit_pair(bar_empty(stage), 3);
+          }
+          __syncwarp();
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        if (elect_one()) umma_commit_pair(bar_accfull(buf), 3);
+        __syncwarp();
+        ++acc_use;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps (both CTAs)
+    const uint32_t q = warp & 3;
+    const uint32_t h = (warp - 2) >> 2;
+    const uint32_t row_in_tile = q * 32 + lane;
+    uint32_t acc_use = 0;
+    for (int item = pair; item < p.num_items; item += num_pairs) {
+      int rb, dt, ks, kb0, kb1;
+      decode(item, rb, dt, ks, kb0, kb1);
+      const uint32_t buf = acc_use & 1, use = acc_use >> 1;
+      mbar_wait(bar_accfull(buf), use & 1);
+      tc_fence_after();
+      const int grow = rb * 2 * kBM + (int)cta * kBM + row_in_tile;
+      float* out_row = p.dpart + ((size_t)ks * p.m_pad + grow) * p.d_pad + dt * kGemmBN;
+      float mul = 1.f;
+      if (p.out != nullptr) {
+        mul = p.coef * __ldg(p.scale);
+        if (p.grad_out != nullptr) mul *= __ldg(p.grad_out);
+      }
+#pragma unroll 1
+      for (int c0 = h * 128; c0 < (int)(h + 1) * 128; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0, r);
+        tmem_ld_wait();
+        if (p.out != nullptr) {
+          if (grow < p.m_rows) {
+            const int col = dt * kGemmBN + c0;
+            if (p.out_dtype == DT_F32) {
+              float* o = reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col;
+              if (col + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  *reinterpret_cast<float4*>(o + 4 * j) =
+                      make_float4(__uint_as_float(r[4 * j]) * mul, __uint_as_float(r[4 * j + 1]) * mul,
+                                  __uint_as_float(r[4 * j + 2]) * mul, __uint_as_float(r[4 * j + 3]) * mul);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (col + j < p.d_valid) o[j] = __uint_as_float(r[j]) * mul;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col + j < p.d_valid)
+                  store_from_float(p.out, p.out_dtype, (size_t)grow * p.out_ld + col + j, __uint_as_float(r[j]) * mul);
+            }
+          }
+        } else if (grow < p.m_rows) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o;
+            o.x = __uint_as_float(r[4 * j + 0]);
+            o.y = __uint_as_float(r[4 * j + 1]);
+            o.z = __uint_as_float(r[4 * j + 2]);
+            o.w = __uint_as_float(r[4 * j + 3]);
+            *reinterpret_cast<float4*>(out_row + c0 + 4 * j) = o;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_shared(bar_accempty(buf), 0));
+      ++acc_use;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();      // nobody frees TMEM or exits while the peer may still signal / read
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_pair(tmem_base, 512);
+  }
+}
+
+}  // namespace mrclip

@@ -2,6 +2,7 @@
 // carving) and kernel launches.  See include/mrclip.h for the contract.
 #include "../../include/mrclip.h"
 #include "aux_kernels.cuh"
+#include "gemm2_kernel.cuh"
 #include "gemm_kernel.cuh"
 #include "tile_kernel.cuh"
 
@@ -148,15 +149,25 @@ BwdPlan bwd_plan(int m_rows, int n_cols, int ld) {
 struct GemmPlan {
   int num_rb, num_dt, num_kb, ksplit, kb_per_split, num_items, m_pad, d_pad;
 };
+// gradient GEMMs run on CTA pairs (gemm2_kernel, 256 x 256 tiles) unless MRCLIP_GEMM_CTA=1
+bool gemm_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("MRCLIP_GEMM_CTA");
+    v = (e && atoi(e) == 1) ? 0 : 1;
+  }
+  return v == 1;
+}
 // out_rows = rows of the gradient being produced, k_len = length of the contraction
 GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
   GemmPlan g;
-  g.num_rb = ceil_div(out_rows, kBM);
+  const int rows_per_item = gemm_pairs() ? 2 * kBM : kBM;
+  g.num_rb = ceil_div(out_rows, rows_per_item);
   g.num_dt = ceil_div(ld, kGemmBN);
   g.num_kb = ceil_div(k_len, kBK);
-  g.m_pad = g.num_rb * kBM;
+  g.m_pad = g.num_rb * rows_per_item;
   g.d_pad = g.num_dt * kGemmBN;
-  const int sms = num_sms();
+  const int sms = gemm_pairs() ? num_sms() / 2 : num_sms();   // schedulable units: CTA pairs or CTAs
   const int base = g.num_rb * g.num_dt;
   int best = 1;
   double best_eff = 0.0;
@@ -381,7 +392,25 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
 }
 
 template <bool A_MN>
+int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm2_kernel<A_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes));
+    attr_set = true;
+  }
+  const int pairs_avail = num_sms() / 2;
+  const int pairs = p.num_items < pairs_avail ? p.num_items : pairs_avail;
+  if (pairs <= 0) return 0;
+  kern<<<2 * pairs, kThreads, kG2SmemBytes, st>>>(ma, mb, p);   // __cluster_dims__(2,1,1)
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+template <bool A_MN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
+  if (gemm_pairs()) return launch_gemm2<A_MN>(ma, mb, p, st);
   auto kern = gemm_kernel<A_MN>;
   static bool attr_set = false;
   if (!attr_set) {
