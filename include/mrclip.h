@@ -158,6 +158,19 @@ int mrclip_emat_transform(mrclip_shape shape, void* ws, void* emat, const float*
 int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
                          const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype, long out_ld,
                          const void* dot_feat, float* dot_out, void* stream);
+/* ---- fused GEMM -> reduce-scatter over NVLink peer memory ------------------------------------------------
+ * The text gradient of rank q is the sum over ranks r of  G_r^T . I_r  restricted to q's rows.  Instead of writing
+ * the [n_cols, d] partial locally and calling a reduce-scatter, the transposed GEMM's epilogue stores every output
+ * tile straight into its owner's receive buffer:  peer_bufs[q] (device array of `ranks` pointers, each the
+ * NVLink-mapped address of rank q's fp32 [ranks][n_per_rank][d] buffer), slot my_rank -- the transfer overlaps the
+ * MMA tile by tile.  After a cross-rank barrier (caller) mrclip_sum_slots adds the `ranks` slots on the owner.
+ * Replaces torch/distributed/nn/functional.py:343-347 (_AllGather.backward's reduce_scatter) for the text side. */
+int mrclip_gmat_gemm_push(const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                          const float* scale, const float* grad_out, void* ws, const unsigned long long* peer_bufs,
+                          int n_per_rank, int my_rank, void* stream);
+int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                     void* stream);
+
 /* SigLipLoss has no normaliser: its forward can store G = sigmoid(z) - [j==label_i] directly (then both
  * gradients are plain mrclip_gmat_gemm calls) and leaves the d_scale / d_bias partial sums in ws. */
 int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,

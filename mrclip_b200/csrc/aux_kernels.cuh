@@ -494,6 +494,20 @@ __global__ void emat_fallback_sums_kernel(const int* __restrict__ run_if, const 
   atomicAdd(msums + ranks + r, y * to_log2);
 }
 
+// out[r, c] = sum_k slots[k][r][c]  (the owner's side of the fused reduce-scatter: W partial slots -> gradient)
+__global__ void sum_slots_kernel(const float* __restrict__ slots, int nslots, int rows, int d,
+                                 void* __restrict__ out, int out_dtype, long out_ld) {
+  const long total = (long)rows * d;
+  const long slot_stride = total;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nslots; ++k) a += slots[k * slot_stride + i];
+    const long r = i / d;
+    const int c = (int)(i - r * d);
+    store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
+  }
+}
+
 __global__ void fill_kernel(float* __restrict__ p, long n, float v) {
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
     p[i] = v;

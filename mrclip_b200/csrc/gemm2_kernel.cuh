@@ -175,7 +175,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (grow < p.m_rows) {
             const int col = dt * kGemmBN + c0;
             if (p.out_dtype == DT_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col;
+              float* o = gemm_out_row_f32(p, grow) + col;
               if (col + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)

@@ -42,7 +42,18 @@ struct GemmParams {
   float coef;
   const float* scale;
   const float* grad_out;   // may be NULL
+  // fused reduce-scatter ("push"): output row block q (peer_n rows) goes straight into rank q's receive buffer,
+  // slot peer_rank, through the NVLink-mapped pointer peer[q]: fp32 [ranks][peer_n][d_valid] on every rank
+  const unsigned long long* peer;
+  int peer_n, peer_rank;
 };
+
+// destination row of the direct epilogue: local output, or the owner's receive slot over NVLink
+__device__ __forceinline__ float* gemm_out_row_f32(const GemmParams& p, int grow) {
+  if (p.peer == nullptr) return reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld;
+  const int q = grow / p.peer_n, lrow = grow - q * p.peer_n;
+  return reinterpret_cast<float*>(__ldg(p.peer + q)) + ((size_t)p.peer_rank * p.peer_n + lrow) * p.out_ld;
+}
 
 // MN-major (M contiguous) A operand tile: K rows of 128 bytes (64 M-elements), 128B swizzle.
 // Two 64-wide M chunks per 128-row A tile, LBO bytes apart; 8 K-rows per swizzle atom (SBO=1024).
@@ -212,7 +223,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (grow < p.m_rows) {
             const int col = dt * kGemmBN + c0;
             if (p.out_dtype == DT_F32) {
-              float* o = reinterpret_cast<float*>(p.out) + (size_t)grow * p.out_ld + col;
+              float* o = gemm_out_row_f32(p, grow) + col;
               if (col + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j)

@@ -159,7 +159,7 @@ bool gemm_pairs() {
   return v == 1;
 }
 // out_rows = rows of the gradient being produced, k_len = length of the contraction
-GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
+GemmPlan gemm_plan(int out_rows, int k_len, int ld, bool force_single_split = false) {
   GemmPlan g;
   const int rows_per_item = gemm_pairs() ? 2 * kBM : kBM;
   g.num_rb = ceil_div(out_rows, rows_per_item);
@@ -175,6 +175,7 @@ GemmPlan gemm_plan(int out_rows, int k_len, int ld) {
   // split-K partials would cost more HBM traffic than the wave quantisation they repair -> one split, and the
   // GEMM's epilogue scales and stores the result itself
   int max_ks = (g.num_kb <= 128 && base >= 3 * sms) ? 1 : 16;
+  if (force_single_split) max_ks = 1;
   if (const char* e = getenv("MRCLIP_GEMM_MAX_KSPLIT")) {   // test / experiment knob
     const int v = atoi(e);
     if (v >= 1 && v <= 16) max_ks = v;
@@ -475,13 +476,16 @@ int run_gwrite(int loss_kind, const void* a_rows, const void* b_all, const mrcli
 struct DotArgs {   // optional: dot_out += <d_out, dot_feat> / scale  (d(loss)/d(scale) by homogeneity)
   const void* dot_feat = nullptr;
   float* dot_out = nullptr;
+  // optional: fused reduce-scatter, see GemmParams::peer
+  const unsigned long long* peer = nullptr;
+  int peer_n = 0, peer_rank = 0;
 };
 int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* feat, int d, int ld,
                   float coef, const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype,
                   long out_ld, const DotArgs& xf, cudaStream_t st) {
   const int out_rows = transposed ? g_cols : g_rows;
   const int k_len = transposed ? g_rows : g_cols;
-  const GemmPlan g = gemm_plan(out_rows, k_len, ld);
+  const GemmPlan g = gemm_plan(out_rows, k_len, ld, xf.peer != nullptr);
   const long g_ld = mrclip_padded_cols(g_cols);
   CUtensorMap ma, mb;
   if (int e = make_map(&ma, gmat, g_rows, g_cols, g_ld, transposed ? 64 : kBM)) return e;
@@ -499,7 +503,11 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
   p.d_pad = g.d_pad;
   p.dpart = reinterpret_cast<float*>(ws);
   const bool direct = (g.ksplit == 1 && xf.dot_feat == nullptr);
+  if (xf.peer && !direct) return fail(-1, "push epilogue needs a single-split GEMM");
   if (direct) {
+    p.peer = xf.peer;
+    p.peer_n = xf.peer_n;
+    p.peer_rank = xf.peer_rank;
     p.out = d_out;
     p.out_ld = out_ld;
     p.out_dtype = out_dtype;
@@ -805,6 +813,35 @@ int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, c
   xf.dot_out = dot_out;
   return run_gmat_gemm(transposed != 0, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out,
                        ws, d_out, out_dtype, out_ld, xf, (cudaStream_t)stream);
+}
+
+int mrclip_gmat_gemm_push(const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                          const float* scale, const float* grad_out, void* ws, const unsigned long long* peer_bufs,
+                          int n_per_rank, int my_rank, void* stream) {
+  if (int e = check_shape(shape, ld)) return e;
+  if (!peer_bufs || n_per_rank <= 0 || shape.n_cols % n_per_rank != 0 || my_rank < 0 ||
+      my_rank >= shape.n_cols / n_per_rank)
+    return fail(-1, "gmat_gemm_push: bad peer layout (n_per_rank=%d, rank=%d, n_cols=%d)", n_per_rank, my_rank, shape.n_cols);
+  DotArgs xf;
+  xf.peer = peer_bufs;
+  xf.peer_n = n_per_rank;
+  xf.peer_rank = my_rank;
+  // d_out only marks the epilogue as direct; rows are routed through peer_bufs (dense fp32, leading dim d)
+  return run_gmat_gemm(true, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out, ws,
+                       const_cast<unsigned long long*>(peer_bufs), MRCLIP_DT_F32, shape.d, xf, (cudaStream_t)stream);
+}
+
+int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                     void* stream) {
+  if (!slots || !out || nslots <= 0 || rows <= 0 || d <= 0) return fail(-1, "sum_slots: bad arguments");
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  const long total = (long)rows * d;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  sum_slots_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(slots, nslots, rows, d, out, out_dtype, out_ld);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,

@@ -155,6 +155,19 @@ class CudaEngine:
                                                   d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0),
                                                   _ptr(dot_feat), _ptr(dot_out), self._stream()))
 
+    def gmat_gemm_push(self, gmat, shape, feat, coef, scale, grad_out, ws, peer_ptrs, n_per_rank, my_rank):
+        """G^T . A with the epilogue scattering row block q into rank q's receive buffer (peer_ptrs: int64 device
+        tensor of NVLink-mapped addresses), slot my_rank."""
+        _cabi.check(self.lib.mrclip_gmat_gemm_push(gmat.data_ptr(), shape, feat.data_ptr(), feat.shape[1], coef,
+                                                   scale.data_ptr(), _ptr(grad_out), ws.data_ptr(),
+                                                   peer_ptrs.data_ptr(), n_per_rank, my_rank, self._stream()))
+
+    def sum_slots(self, slots, d_out):
+        """d_out[rows, d] = sum_k slots[k] (fp32 [k, rows, d] contiguous)."""
+        assert slots.dtype == torch.float32 and slots.is_contiguous() and slots.dim() == 3
+        _cabi.check(self.lib.mrclip_sum_slots(slots.data_ptr(), slots.shape[0], slots.shape[1], slots.shape[2],
+                                              d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0), self._stream()))
+
     def siglip_fwd_e(self, a_rows, b_all, shape, scale, bias, ws, loss, gmat):
         _cabi.check(self.lib.mrclip_siglip_fwd_e(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
                                                  scale.data_ptr(), _ptr(bias), ws.data_ptr(), loss.data_ptr(),

@@ -134,6 +134,7 @@ class _Workspace:
         self.transposed = False
         self.gmat = None
         self.dt_partial = None
+        self.push = None
         self.msums = torch.zeros((2, world), dtype=f32, device=device)
         self.has_emat = False
 
@@ -143,6 +144,24 @@ class _Workspace:
             nbytes = int(eng.gmat_bytes(self.n, self.N))
             self.gmat = torch.empty(max(nbytes // 2, 8), dtype=torch.bfloat16, device=self.img_all.device)
         return self.gmat
+
+    def push_buffers(self, rank):
+        """Peer-mapped receive buffer of the fused GEMM -> reduce-scatter (fp32 [W, n, d] on every rank, symmetric
+        memory over NVLink): returns (recv, int64 device tensor of every rank's mapped address, handle), or None when
+        symmetric memory is unavailable (then NCCL's reduce_scatter is used).  Collective on first use."""
+        if self.push is None:
+            self.push = False
+            if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "nccl").lower() == "push":
+                try:
+                    import torch.distributed._symmetric_memory as symm_mem
+                    recv = symm_mem.empty((self.world, self.n, self.d), dtype=torch.float32, device=self.img_all.device)
+                    hdl = symm_mem.rendezvous(recv, dist.group.WORLD)
+                    ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.img_all.device)
+                    self.push = (recv, ptrs, hdl)
+                except Exception as exc:  # pragma: no cover  (depends on the driver / fabric setup of the box)
+                    import warnings
+                    warnings.warn(f"mrclip_b200: symmetric memory unavailable ({exc}); using NCCL reduce_scatter")
+        return self.push or None
 
     def dt_partial_buffer(self):
         """fp32 [N, d] partial text gradient of this rank's row block (reduce-scattered), world > 1 only."""
@@ -245,6 +264,36 @@ def _ensure_transposed(eng, ws):
         ws.transposed = True
 
 
+def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
+    """dT_r = sum over ranks q of (G_q^T . I_q)[rows of r].  Launches this rank's partial GEMM and returns the
+    closure that completes d_txt; the caller runs the image-gradient GEMM in between.
+
+    MRCLIP_RS=push: the GEMM's epilogue pushes each output tile into its owner's receive slot over NVLink peer
+    memory (csrc/gemm2_kernel.cuh, mrclip_gmat_gemm_push), then one device-side barrier and a slot sum on the owner.
+    Default (and CPU tests under gloo): fp32 partial + NCCL reduce_scatter, asynchronous, overlapped with the
+    image-gradient GEMM -- measured faster on 4 and 8 B200s (profiles/r1_notes.md)."""
+    n, d, world = ws.n, ws.d, ws.world
+    rows = slice(rank * n, (rank + 1) * n)
+    push = ws.push_buffers(rank)
+    if push is not None:
+        recv, ptrs, hdl = push
+        eng.gmat_gemm_push(gmat, shape, ws.img_all[rows], coef, scale, gout, ws.scratch, ptrs, n, rank)
+
+        def finish():
+            hdl.barrier()                  # every rank's tiles have landed in my slots (and mine in theirs)
+            eng.sum_slots(recv, d_txt)
+        return finish
+    part = ws.dt_partial_buffer()
+    eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, scale, gout, ws.scratch, part)
+    dt32 = torch.empty((n, d), dtype=torch.float32, device=part.device)
+    work = dist.reduce_scatter_tensor(dt32, part, op=dist.ReduceOp.SUM, async_op=True)
+
+    def finish():
+        work.wait()
+        d_txt.copy_(dt32)
+    return finish
+
+
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, module):
@@ -334,10 +383,7 @@ class _ClipLossFn(torch.autograd.Function):
                     ds_done = True
             else:
                 # text gradient: every rank holds G_q^T . I_q for all N text rows; the owner sums them
-                part = ws.dt_partial_buffer()
-                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, part)
-                dt32 = torch.empty((n, d), dtype=torch.float32, device=device)
-                work = dist.reduce_scatter_tensor(dt32, part, op=dist.ReduceOp.SUM, async_op=True)
+                finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt)
                 eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
                 if need_s:
                     # scale * dL_r/dscale = L_r + ln2/(2n) * (sum P log2 P over my rows, row softmax, all columns
@@ -350,8 +396,7 @@ class _ClipLossFn(torch.autograd.Function):
                         dist.all_reduce(ds, op=dist.ReduceOp.SUM)
                         ds = ds / world
                     ds_done = True
-                work.wait()
-                d_txt.copy_(dt32)
+                finish_dt()
         elif _use_gmat(eng, ws):
             gmat = ws.gmat_buffer(eng)
             # image rows vs all texts: G block of this rank's rows -> dI_r
@@ -500,13 +545,9 @@ class _SigLipLossFn(torch.autograd.Function):
                 eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
                 eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
             else:
-                part = ws.dt_partial_buffer()
-                eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, part)
-                dt32 = torch.empty((n, d), dtype=torch.float32, device=device)
-                work = dist.reduce_scatter_tensor(dt32, part, op=dist.ReduceOp.SUM, async_op=True)
+                finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt)
                 eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
-                work.wait()
-                d_txt.copy_(dt32)
+                finish_dt()
         elif _use_gmat(eng, ws):
             gmat = ws.gmat_buffer(eng)
             eng.siglip_gwrite(ws.img_all[rows], ws.txt_all, shape, ctx.scale, ctx.bias, coef, gout, ws.scratch, gmat,

@@ -30,8 +30,10 @@ def main():
         case = load_golden(name)
         m = case["meta"]
         assert case["world"] == world, (name, case["world"], world)
-        for backend in ("emat", "gmat", "fused"):
-            os.environ["MRCLIP_BWD"] = backend
+        # emat: text gradient through the GEMM's peer-memory push epilogue; emat-nccl: through reduce_scatter
+        for backend in ("emat", "emat-nccl", "gmat", "fused"):
+            os.environ["MRCLIP_BWD"] = backend.split("-")[0]
+            os.environ["MRCLIP_RS"] = "nccl" if backend.endswith("-nccl") else "push"
             n = case["image"].shape[0] // world
             rows = slice(rank * n, (rank + 1) * n)
             i = torch.from_numpy(case["image"][rows]).to(dev).requires_grad_(True)
@@ -59,7 +61,7 @@ def main():
             if bad:
                 failures.append((name, backend, rank, bad, errs))
             if rank == 0:
-                print(f"{name:32s} {backend:5s} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+                print(f"{name:32s} {backend:9s} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     for f in failures:
