@@ -200,11 +200,12 @@ def run_ours(args):
     # launching stream; the roofline is quoted for the costliest op that carries algorithmic flops
     ALG_OPS = {"clip_fwd_tiles": "tile_kernel<MODE_FWD> (S = A.B^T tiles + online LSE, 2nND flop)",
                "clip_fwd_tiles_e": "tile_kernel<MODE_FWDE> (S = A.B^T tiles + online LSE + bf16 E block out, 2nND flop)",
-               "gmat_gemm": "gemm_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, 2nND flop per launch)",
-               "gmat_gemm_dot": "gemm_kernel (dA = G.B from the bf16 gradient block, 2nND flop per launch)",
+               "gmat_gemm": "gemm2_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
+               "gmat_gemm_dot": "gemm2_kernel (dA = G.B from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
+               "gmat_gemm_push": "gemm2_kernel<PUSH> (dB partial = G^T.A, tiles pushed to their owner over NVLink, 2nND flop)",
                "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)"}
     TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "clip_fwd_reduce", "lse2_merge", "clip_loss",
-             "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "clip_bwd"]
+             "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "gmat_gemm_push", "sum_slots", "clip_bwd"]
     ev = {k: [] for k in TIMED}
     originals = {k: getattr(eng, k) for k in TIMED}
 
@@ -220,12 +221,30 @@ def run_ours(args):
 
     for k in TIMED:
         setattr(eng, k, wrap(k, originals[k]))
+    # multi-rank: how long each collective holds up the launching stream (issue -> the stream may proceed)
+    COMM = ["all_gather_into_tensor", "reduce_scatter_tensor", "all_reduce"] if world > 1 else []
+    comm_orig = {k: getattr(dist, k) for k in COMM}
+    for k in COMM:
+        ev["comm:" + k] = []
+
+        def make(name, fn):
+            def inner(*a, **kw):
+                s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s0.record()
+                r = fn(*a, **kw)
+                s1.record()
+                ev["comm:" + name].append((s0, s1))
+                return r
+            return inner
+        setattr(dist, k, make(k, comm_orig[k]))
     prof_steps = min(args.steps, 10)
     for _ in range(prof_steps):
         step(img_d, txt_d)
     torch.cuda.synchronize()
     for k in TIMED:
         setattr(eng, k, originals[k])
+    for k in COMM:
+        setattr(dist, k, comm_orig[k])
     per_op_ms = {k: sum(a.elapsed_time(b) for a, b in v) / prof_steps for k, v in ev.items() if v}
     per_op_calls = {k: len(v) // prof_steps for k, v in ev.items() if v}
     dom = max((k for k in per_op_ms if k in ALG_OPS), key=lambda k: per_op_ms[k])

@@ -17,16 +17,23 @@
 namespace mrclip {
 
 constexpr int kG2StageBytes = 16384 + 16384;
-constexpr int kG2Stages = 6;
-constexpr int kG2Bars = 2 * kG2Stages + 4;
-constexpr int kG2SmemBytes = kG2Stages * kG2StageBytes + kG2Bars * 8 + 16 + 1024;
+constexpr int kG2Bars = 2 * 6 + 4;
+// PUSH (fused reduce-scatter): one ring stage is traded for a 32 x 32 fp32 staging tile per epilogue warp (rows
+// padded to 144 B against bank conflicts), from which every lane sends its row as one 128-byte bulk copy -- peer
+// memory over NVLink wants full-line packets, 16-byte stores from the registers reached a fraction of the link rate
+constexpr int kG2PushRowBytes = 144;
+template <bool PUSH> struct G2Cfg {
+  static constexpr int kStages = PUSH ? 5 : 6;
+  static constexpr int kStagingBytes = PUSH ? kEpiWarps * 32 * kG2PushRowBytes : 0;
+  static constexpr int kSmemBytes = kStages * kG2StageBytes + kStagingBytes + kG2Bars * 8 + 16 + 1024;
+};
 
 // GemmParams::num_rb counts 256-row pair blocks here.
-template <bool A_MN>
+template <bool A_MN, bool PUSH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const GemmParams p) {
-  constexpr int STAGES = kG2Stages;
+  constexpr int STAGES = G2Cfg<PUSH>::kStages;
   // M = 256 across the pair; bit 15 = A is MN-major, bit 16 = B is MN-major
   constexpr uint32_t IDESC = make_idesc_bf16(2 * kBM, kGemmBN) | (A_MN ? (1u << 15) : 0u) | (1u << 16);
 
@@ -34,7 +41,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
   const uint32_t stage_base = smem_u32(smem);
-  uint8_t* bar_ptr = smem + STAGES * kG2StageBytes;
+  const uint32_t staging_base = stage_base + STAGES * kG2StageBytes;
+  uint8_t* bar_ptr = smem + STAGES * kG2StageBytes + G2Cfg<PUSH>::kStagingBytes;
   const uint32_t bar_base = smem_u32(bar_ptr);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + kG2Bars * 8);
   auto bar_full = [&](int s) { return bar_base + 8u * s; };
@@ -171,7 +179,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0, r);
         tmem_ld_wait();
-        if (p.out != nullptr) {
+        if (PUSH && p.peer != nullptr && dt * kGemmBN + c0 + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
+          // push epilogue: scale into the warp's staging tile, then one 128-byte bulk copy per row to the owner
+          const uint32_t my_row = staging_base + ((warp - 2) * 32 + lane) * kG2PushRowBytes;
+          bulk_wait_read0();                       // this lane's previous row has left the staging tile
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_f4(my_row + 16 * j,
+                   make_float4(__uint_as_float(r[4 * j]) * mul, __uint_as_float(r[4 * j + 1]) * mul,
+                               __uint_as_float(r[4 * j + 2]) * mul, __uint_as_float(r[4 * j + 3]) * mul));
+          fence_proxy_async_smem();
+          if (grow < p.m_rows) {
+            bulk_store(gemm_out_row_f32(p, grow) + dt * kGemmBN + c0, my_row, 128);
+            bulk_commit();
+          }
+        } else if (p.out != nullptr) {
           if (grow < p.m_rows) {
             const int col = dt * kGemmBN + c0;
             if (p.out_dtype == DT_F32) {
@@ -211,6 +233,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (lane == 0) mbar_arrive_cluster(mapa_shared(bar_accempty(buf), 0));
       ++acc_use;
     }
+    if (PUSH) bulk_wait0();   // every pushed row is complete before the kernel (and the cross-rank barrier) ends
   }
   tc_fence_before();
   __syncthreads();

@@ -392,9 +392,10 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
   return 0;
 }
 
-template <bool A_MN>
+template <bool A_MN, bool PUSH>
 int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm2_kernel<A_MN>;
+  auto kern = gemm2_kernel<A_MN, PUSH>;
+  constexpr int kG2SmemBytes = G2Cfg<PUSH>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes));
@@ -411,7 +412,7 @@ int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams&
 
 template <bool A_MN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  if (gemm_pairs()) return launch_gemm2<A_MN>(ma, mb, p, st);
+  if (gemm_pairs()) return p.peer ? launch_gemm2<A_MN, true>(ma, mb, p, st) : launch_gemm2<A_MN, false>(ma, mb, p, st);
   auto kern = gemm_kernel<A_MN>;
   static bool attr_set = false;
   if (!attr_set) {

@@ -427,7 +427,79 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             bulk_commit();
           }
         };
-        if (kFwd && LOSS == LOSS_CLIP) {
+        if (MODE == MODE_FWDE && LOSS == LOSS_CLIP) {
+          // ---- forward that keeps E: the lean epilogue (sl > 0: logit_scale is exp(.) in the reference, model.py:324)
+          //   * the sub-tile reference is taken on the raw accumulators (max commutes with the positive scale), so
+          //     the scaling folds into the exponent's FMA, issued as packed fp32 pairs (FFMA2 / FADD2);
+          //   * the column sums go through the warp's staging tile in fp32 (two 32-column halves, swizzled, conflict
+          //     free: 16 STS.128 + 64 LDS + 64 FADD per lane) instead of a 5-step shuffle butterfly (~250
+          //     instructions); they must stay fp32 -- summing the bf16 E instead loses the column LSE of a confident
+          //     model (dominant term rounded to 8 bits) and with it the loss.
+          float a[64];
+#pragma unroll
+          for (int c = 0; c < 64; ++c) a[c] = __uint_as_float(raw[c]);
+          if (diag_here && row_valid) {
+            const int idx = label - col_base;
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (c == idx) p.diag2[grow] = a[c] * sl;
+          }
+          if (ragged) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              if (col_base + c >= p.n_cols) a[c] = -CUDART_INF_F;
+          }
+          if (!row_valid) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) a[c] = -CUDART_INF_F;
+          }
+          float tmax = a[0];
+#pragma unroll
+          for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, a[c]);
+          const float wmax = warp_max(tmax);
+          const float cw = (wmax == -CUDART_INF_F) ? 0.f : wmax * sl;
+          const float2 sl2 = make_float2(sl, sl), ncw2 = make_float2(-cw, -cw);
+          float2 rs2 = make_float2(0.f, 0.f);
+          float v[64];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float2 t = ffma2(make_float2(a[2 * c], a[2 * c + 1]), sl2, ncw2);
+            v[2 * c] = ex2f(t.x);
+            v[2 * c + 1] = ex2f(t.y);
+            rs2 = fadd2(rs2, make_float2(v[2 * c], v[2 * c + 1]));
+          }
+          const float rowsum = rs2.x + rs2.y;
+          const float mnew = fmaxf(m_run, cw);
+          l_run = l_run * ex2f(m_run - mnew) + rowsum * ex2f(cw - mnew);
+          m_run = mnew;
+          // column sums: lane = row writes 32 fp32 columns (8 swizzled 16-byte chunks), then lane = column reads them
+          const uint32_t stg = e_smem + (warp - 2) * 4096;
+          if (lane == 0) bulk_wait_read0();   // the previous E tile of this warp has left the staging buffer
+          float cs[2];
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf) {
+            __syncwarp();
+#pragma unroll
+            for (int ck = 0; ck < 8; ++ck)
+              sts_f4(stg + lane * 128 + ((static_cast<uint32_t>(ck) ^ (lane & 7)) << 4),
+                     make_float4(v[hf * 32 + ck * 4], v[hf * 32 + ck * 4 + 1], v[hf * 32 + ck * 4 + 2],
+                                 v[hf * 32 + ck * 4 + 3]));
+            __syncwarp();
+            float acc = 0.f;
+#pragma unroll
+            for (int r8 = 0; r8 < 8; ++r8) {
+              const uint32_t base = stg + r8 * 128 + ((((lane >> 2) ^ r8)) << 4) + (lane & 3) * 4;
+#pragma unroll
+              for (int r = 0; r < 4; ++r) acc += __uint_as_float(lds_u32(base + r * 1024));
+            }
+            cs[hf] = acc;
+          }
+          store_e(v);   // bf16 E through the same staging tile (its __syncwarp orders it after the column reads)
+          const int band = rb * 4 + q;
+          p.col_l[(size_t)band * p.n_pad + col_base + lane] = cs[0];
+          p.col_l[(size_t)band * p.n_pad + col_base + 32 + lane] = cs[1];
+          if (lane == 0) p.col_c[(size_t)band * (p.n_pad / 64) + col_base / 64] = cw;
+        } else if (kFwd && LOSS == LOSS_CLIP) {
           float v[64];
 #pragma unroll
           for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(raw[c]) * sl;

@@ -151,7 +151,7 @@ class _Workspace:
         symmetric memory is unavailable (then NCCL's reduce_scatter is used).  Collective on first use."""
         if self.push is None:
             self.push = False
-            if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "nccl").lower() == "push":
+            if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "push").lower() != "nccl":
                 try:
                     import torch.distributed._symmetric_memory as symm_mem
                     recv = symm_mem.empty((self.world, self.n, self.d), dtype=torch.float32, device=self.img_all.device)
@@ -268,10 +268,10 @@ def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
     """dT_r = sum over ranks q of (G_q^T . I_q)[rows of r].  Launches this rank's partial GEMM and returns the
     closure that completes d_txt; the caller runs the image-gradient GEMM in between.
 
-    MRCLIP_RS=push: the GEMM's epilogue pushes each output tile into its owner's receive slot over NVLink peer
-    memory (csrc/gemm2_kernel.cuh, mrclip_gmat_gemm_push), then one device-side barrier and a slot sum on the owner.
-    Default (and CPU tests under gloo): fp32 partial + NCCL reduce_scatter, asynchronous, overlapped with the
-    image-gradient GEMM -- measured faster on 4 and 8 B200s (profiles/r1_notes.md)."""
+    Default on GPUs: the GEMM's epilogue pushes each output tile into its owner's receive slot over NVLink peer
+    memory (csrc/gemm2_kernel.cuh, mrclip_gmat_gemm_push: 128-byte bulk copies from a staging tile), then one
+    device-side barrier and a slot sum on the owner.  MRCLIP_RS=nccl, CPU tests under gloo, or no symmetric memory:
+    fp32 partial + reduce_scatter, asynchronous, overlapped with the image-gradient GEMM."""
     n, d, world = ws.n, ws.d, ws.world
     rows = slice(rank * n, (rank + 1) * n)
     push = ws.push_buffers(rank)
@@ -382,14 +382,17 @@ class _ClipLossFn(torch.autograd.Function):
                     ds = (gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ws.msums.sum())
                     ds_done = True
             else:
+                colsum = work_cs = None
+                if need_s:   # column-softmax entropies of my columns live on every rank: W-float all-reduce, async
+                    colsum = ws.msums[1].clone()
+                    work_cs = dist.all_reduce(colsum, op=dist.ReduceOp.SUM, async_op=True)
                 # text gradient: every rank holds G_q^T . I_q for all N text rows; the owner sums them
                 finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt)
                 eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
                 if need_s:
                     # scale * dL_r/dscale = L_r + ln2/(2n) * (sum P log2 P over my rows, row softmax, all columns
                     #                                         + over my columns, column softmax, all rows)
-                    colsum = ws.msums[1].clone()
-                    dist.all_reduce(colsum, op=dist.ReduceOp.SUM)
+                    work_cs.wait()
                     ent = ws.msums[0].sum() + colsum[rank]
                     ds = ((gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ent)).reshape(1)
                     if not module.local_loss:
