@@ -168,6 +168,12 @@ int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, c
 int mrclip_gmat_gemm_push(const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
                           const float* scale, const float* grad_out, void* ws, const unsigned long long* peer_bufs,
                           int n_per_rank, int my_rank, void* stream);
+/* All-gather by peer stores: copies `bytes` from src into peer_bufs[k] + dst_offset for every rank k != skip_rank
+ * (peer_bufs: device array of NVLink-mapped addresses of the same buffer on every rank).  Replaces the NCCL
+ * all-gathers of loss.py:51-57 for the packed features and the LSE statistics; the caller follows it with a
+ * cross-rank barrier. */
+int mrclip_push_copy(const void* src, size_t bytes, const unsigned long long* peer_bufs, int ranks, size_t dst_offset,
+                     int skip_rank, void* stream);
 int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
                      void* stream);
 

@@ -51,6 +51,7 @@ SIGNATURES = {
     "mrclip_siglip_fwd_e": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P]),
     "mrclip_siglip_e_scalars": (_I, [Shape, _P, _F, _P, _P, _P, _I, _P]),
     "mrclip_gmat_gemm_push": (_I, [_P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _I, _P]),
+    "mrclip_push_copy": (_I, [_P, C.c_size_t, _P, _I, C.c_size_t, _I, _P]),
     "mrclip_sum_slots": (_I, [_P, _I, _I, _I, _P, _I, _L, _P]),
     "mrclip_launch_count": (_L, []),
 }

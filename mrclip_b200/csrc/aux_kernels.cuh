@@ -404,30 +404,33 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
         const float4 l0 = *reinterpret_cast<const float4*>(lcol + c);
         const float4 l1 = *reinterpret_cast<const float4*>(lcol + c + 4);
         const float df[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        // w * P * log2 P per element, both directions, with t = e log2 e (0 for flushed / padded entries):
-        //   row: rf * (t + e * (c - lr))        col: cfac * t + dfac * e
+        // w * P * log2 P with t = e log2 e (0 for flushed / padded entries; the positive is taken out and added
+        // back exactly):   row: rf * (sum t + (c - lr) * sum e)        col: sum (cfac * t + dfac * e)
         const float dr = (rf > 0.f) ? cw - lr : 0.f;
-        float tr[8], tc[8];
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
-          tr[k] = (k == kd) ? trd : rf * fmaf(e[k], dr, t);
-          tc[k] = (k == kd) ? tcd : fmaf(cf[k], t, df[k] * e[k]);
-        }
         if (ks[seg] == 8) {
+          float st = 0.f, se = 0.f, sc = 0.f;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            acc_lo_r[seg] += tr[k];
-            acc_lo_c[seg] += tc[k];
+            const float ek = (k == kd) ? 0.f : e[k];
+            const float t = ek * fmaxf(lg2f(ek), -200.f);
+            st += t;
+            se += ek;
+            sc = fmaf(cf[k], t, sc);
+            sc = fmaf(df[k], ek, sc);
           }
-        } else {
+          acc_lo_r[seg] += fmaf(rf, fmaf(dr, se, st), trd);
+          acc_lo_c[seg] += sc + tcd;
+        } else {   // a rank boundary inside these 8 columns (n not a multiple of 8): element by element
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
+            const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
+            const float tr = (k == kd) ? trd : rf * fmaf(e[k], dr, t);
+            const float tc = (k == kd) ? tcd : fmaf(cf[k], t, df[k] * e[k]);
             const bool lo = k < ks[seg];
-            acc_lo_r[seg] += lo ? tr[k] : 0.f;
-            acc_lo_c[seg] += lo ? tc[k] : 0.f;
-            acc_hi_r[seg] += lo ? 0.f : tr[k];
-            acc_hi_c[seg] += lo ? 0.f : tc[k];
+            acc_lo_r[seg] += lo ? tr : 0.f;
+            acc_lo_c[seg] += lo ? tc : 0.f;
+            acc_hi_r[seg] += lo ? 0.f : tr;
+            acc_hi_c[seg] += lo ? 0.f : tc;
           }
         }
       }
@@ -506,6 +509,18 @@ __global__ void sum_slots_kernel(const float* __restrict__ slots, int nslots, in
     const int c = (int)(i - r * d);
     store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
   }
+}
+
+// all-gather by peer stores: copy `bytes` (multiple of 16) from src to dst[k] + offset for every k != skip.
+// dsts are NVLink-mapped addresses of the same buffer on every rank; a warp writes 512 contiguous bytes, so the
+// link sees full 128-byte packets.  grid.y = destination.
+__global__ void push_copy_kernel(const uint4* __restrict__ src, long n16, const unsigned long long* __restrict__ dsts,
+                                 long offset_bytes, int skip) {
+  const int k = blockIdx.y;
+  if (k == skip) return;
+  uint4* dst = reinterpret_cast<uint4*>(__ldg(dsts + k) + offset_bytes);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x)
+    dst[i] = src[i];
 }
 
 __global__ void fill_kernel(float* __restrict__ p, long n, float v) {

@@ -832,6 +832,23 @@ int mrclip_gmat_gemm_push(const void* gmat, mrclip_shape shape, const void* feat
                        const_cast<unsigned long long*>(peer_bufs), MRCLIP_DT_F32, shape.d, xf, (cudaStream_t)stream);
 }
 
+int mrclip_push_copy(const void* src, size_t bytes, const unsigned long long* peer_bufs, int ranks, size_t dst_offset,
+                     int skip_rank, void* stream) {
+  if (!src || !peer_bufs || ranks <= 0 || bytes == 0) return fail(-1, "push_copy: bad arguments");
+  if ((bytes & 15) || (dst_offset & 15) || (reinterpret_cast<uintptr_t>(src) & 15))
+    return fail(-1, "push_copy: 16-byte alignment required (bytes=%zu, offset=%zu)", bytes, dst_offset);
+  const long n16 = (long)(bytes / 16);
+  long bx = (n16 + 255) / 256;
+  const long cap = (148L * 8 + ranks - 1) / ranks;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  push_copy_kernel<<<dim3((unsigned)bx, (unsigned)ranks), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const uint4*>(src), n16, peer_bufs, (long)dst_offset, skip_rank);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
 int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
                      void* stream) {
   if (!slots || !out || nslots <= 0 || rows <= 0 || d <= 0) return fail(-1, "sum_slots: bad arguments");

@@ -162,6 +162,12 @@ class CudaEngine:
                                                    scale.data_ptr(), _ptr(grad_out), ws.data_ptr(),
                                                    peer_ptrs.data_ptr(), n_per_rank, my_rank, self._stream()))
 
+    def push_copy(self, src, peer_ptrs, dst_offset_bytes, skip_rank):
+        """copy the contiguous tensor src into every peer's buffer at dst_offset_bytes (all-gather by NVLink stores)"""
+        assert src.is_contiguous()
+        _cabi.check(self.lib.mrclip_push_copy(src.data_ptr(), src.numel() * src.element_size(), peer_ptrs.data_ptr(),
+                                              peer_ptrs.numel(), dst_offset_bytes, skip_rank, self._stream()))
+
     def sum_slots(self, slots, d_out):
         """d_out[rows, d] = sum_k slots[k] (fp32 [k, rows, d] contiguous)."""
         assert slots.dtype == torch.float32 and slots.is_contiguous() and slots.dim() == 3

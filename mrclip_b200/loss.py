@@ -121,12 +121,20 @@ class _Workspace:
         bf, f32 = torch.bfloat16, torch.float32
         self.img_all = torch.zeros((self.N, self.ld), dtype=bf, device=device)
         self.txt_all = torch.zeros((self.N, self.ld), dtype=bf, device=device)
+        # symmetric (NVLink peer-mapped) twins for the all-gathers by peer stores: two text buffers, alternated per
+        # forward (a peer may still read last step's buffer in its backward), and the statistics block
+        self.sym = None
+        if world > 1 and torch.device(device).type == "cuda" and os.environ.get("MRCLIP_AG", "push").lower() != "nccl":
+            self.sym = _symmetric_buffers(self, device)
+        self.flip = 0
         self.img_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
         self.txt_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
         self.scratch = torch.empty(max(int(eng.workspace_bytes(n, self.N, d)), 256), dtype=torch.uint8, device=device)
         # statistics in log2 units
         self.stats_local = torch.zeros((3, self.N), dtype=f32, device=device)      # col_m, col_l, (row lse2 in [:n])
         self.stats_all = torch.zeros((world, 3, self.N), dtype=f32, device=device) if world > 1 else None
+        if self.sym is not None:
+            self.stats_all = self.sym["stats"][0]
         self.lse2_row_all = torch.full((self.npad,), float("inf"), dtype=f32, device=device)
         self.lse2_col_all = torch.full((self.npad,), float("inf"), dtype=f32, device=device)
         self.diag2 = torch.zeros((n,), dtype=f32, device=device)
@@ -168,6 +176,25 @@ class _Workspace:
         if self.dt_partial is None:
             self.dt_partial = torch.empty((self.N, self.d), dtype=torch.float32, device=self.img_all.device)
         return self.dt_partial
+
+
+def _symmetric_buffers(ws, device):
+    """Collective: every rank allocates the same symmetric buffers in the same order.  None when unavailable."""
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        def make(shape, dtype):
+            t = symm_mem.empty(shape, dtype=dtype, device=device)
+            hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
+            t.zero_()
+            return t, hdl, ptrs
+        return {"txt": [make((ws.N, ws.ld), torch.bfloat16) for _ in range(2)],
+                "stats": make((ws.world, 3, ws.N), torch.float32)}
+    except Exception as exc:  # pragma: no cover  (depends on the driver / fabric setup of the box)
+        import warnings
+        warnings.warn(f"mrclip_b200: symmetric memory unavailable ({exc}); using NCCL all-gathers")
+        return None
 
 
 def _backend(eng, ws):
@@ -241,9 +268,17 @@ def _gather_packed(eng, ws, image_features, text_features, rank, world, gather_i
         img = img.contiguous()
     if txt.stride(1) != 1:
         txt = txt.contiguous()
+    push = world > 1 and ws.sym is not None and not gather_images
+    if push:
+        ws.flip ^= 1
+        ws.txt_all, hdl, ptrs = ws.sym["txt"][ws.flip]
     eng.pack(img, ws.img_all[rows])
     eng.pack(txt, ws.txt_all[rows])
-    if world > 1:
+    if push:
+        # all-gather by peer stores: my packed slice goes straight into every peer's buffer over NVLink
+        eng.push_copy(ws.txt_all[rows], ptrs, rank * n * ws.ld * 2, rank)
+        hdl.barrier()
+    elif world > 1:
         if gather_images:
             _all_gather_rows(ws.img_all, rows)
         _all_gather_rows(ws.txt_all, rows)
@@ -321,8 +356,14 @@ class _ClipLossFn(torch.autograd.Function):
             eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
         col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
         eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
-        if world > 1:
+        if world > 1 and ws.sym is not None and N % 4 == 0:     # (16-byte granular peer stores)
+            _, shdl, sptrs = ws.sym["stats"]
+            ws.stats_all[rank].copy_(ws.stats_local)
+            eng.push_copy(ws.stats_all[rank], sptrs, rank * 3 * N * 4, rank)
+            shdl.barrier()
+        elif world > 1:
             dist.all_gather_into_tensor(ws.stats_all.view(world * 3, N), ws.stats_local)
+        if world > 1:
             eng.lse2_merge(ws.stats_all[0, 0], ws.stats_all[0, 1], world, 3 * N, N, ws.lse2_col_all)
             ws.lse2_row_all[:N].view(world, n).copy_(ws.stats_all[:, 2, :n])
         else:

@@ -30,10 +30,11 @@ def main():
         case = load_golden(name)
         m = case["meta"]
         assert case["world"] == world, (name, case["world"], world)
-        # emat: text gradient through the GEMM's peer-memory push epilogue; emat-nccl: through reduce_scatter
+        # emat: collectives over NVLink peer memory (push all-gathers, GEMM push epilogue); emat-nccl: the same through NCCL
         for backend in ("emat", "emat-nccl", "gmat", "fused"):
             os.environ["MRCLIP_BWD"] = backend.split("-")[0]
             os.environ["MRCLIP_RS"] = "nccl" if backend.endswith("-nccl") else "push"
+            os.environ["MRCLIP_AG"] = os.environ["MRCLIP_RS"]      # all-gathers: NCCL or peer stores, likewise
             n = case["image"].shape[0] // world
             rows = slice(rank * n, (rank + 1) * n)
             i = torch.from_numpy(case["image"][rows]).to(dev).requires_grad_(True)
