@@ -67,7 +67,9 @@ def run_reference(args):
         "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)),
         "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "note": "reference algorithm on host cores (oracle/clip_port.py; "
+        "config": {"workload": workload_name(args), "global_batch": args.global_batch, "dim": args.dim,
+                   "feature_dtype": "fp32", "logit_scale": LOGIT_SCALE,
+                   "note": "reference algorithm on host cores (oracle/clip_port.py; "
                    "the reference is pure PyTorch CPU code and /root/reference is absent on the GPU box)"},
         "cpu_baseline": {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
                          "sample": res["sample"]},

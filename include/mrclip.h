@@ -144,15 +144,16 @@ int mrclip_clip_gwrite_if(const void* a_rows, const void* b_all, mrclip_shape sh
                           const float* lse2_b, const float* scale, float w_own, float w_oth, void* ws, void* gmat,
                           const int* run_if, void* stream);
 /* lse2_row indexes emat rows, lse2_col (padded, +inf) its columns, diag2 its rows.
- * msums (optional, float [2][ranks], zeroed here): what d(loss)/d(logit_scale) needs, split by the rank that
- * owns the column (n_per_rank columns each):
+ * msums (optional, float [msum_slots][2][ranks], zeroed here; the blocks spread their contributions over the slots
+ * and the caller adds the slots up): what d(loss)/d(logit_scale) needs, split by the rank that owns the column
+ * (n_per_rank columns each):
  *   msums[0][r] = sum_{i, j in rank r} w_row * Prow_ij * log2 Prow_ij,   msums[1][r] = same with w_col * Pcol,
  * log2 P recovered as c + log2(E) - lse2 (positives exact).  With L_q the local loss (natural log) of rank q,
  *   scale * dL_q/dscale = L_q + ln2/(2n) * (sum_r msums_q[0][r] + sum_p msums_p[1][q]);
  * with the guard raised the same sums are taken from the exact recompute's partials (chunk granularity). */
 int mrclip_emat_transform(mrclip_shape shape, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
                           const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
-                          float* msums, int n_per_rank, int ranks, void* stream);
+                          float* msums, int msum_slots, int n_per_rank, int ranks, void* stream);
 /* mrclip_gmat_gemm with  dot_out += <d_out, dot_feat> / scale  (dot_feat: bf16 [out_rows, ld]): with d_out = dA and
  * dot_feat = A this is d(loss)/d(scale), by homogeneity of S = scale * A.B^T. */
 int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,

@@ -46,7 +46,7 @@ SIGNATURES = {
     "mrclip_emat_check": (_I, [Shape, _P, _P, _P, _P]),
     "mrclip_emat_flag": (_P, [Shape, _P]),
     "mrclip_clip_gwrite_if": (_I, [_P, _P, Shape, _I, _P, _P, _P, _F, _F, _P, _P, _P, _P]),
-    "mrclip_emat_transform": (_I, [Shape, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _P]),
+    "mrclip_emat_transform": (_I, [Shape, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _I, _I, _I, _P]),
     "mrclip_gmat_gemm_dot": (_I, [_I, _P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _L, _P, _P, _P]),
     "mrclip_siglip_fwd_e": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P]),
     "mrclip_siglip_e_scalars": (_I, [Shape, _P, _F, _P, _P, _P, _I, _P]),

@@ -322,12 +322,16 @@ __global__ void emat_check_kernel(const float* __restrict__ colc, const float* _
 // log2 P = c + log2(E) - lse2 recovered from the stored exponential (positives: exact, from diag2).  The error
 // of a bf16-rounded E then scales with the entropy, not with |S2|, and nothing cancels against an exact term.
 template <bool WSUM>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pad, const float* __restrict__ colc,
                       int ncb, const float* __restrict__ lse2_row, const float* __restrict__ lse2_col,
                       const float* __restrict__ diag2, int label_offset, float w_row, float w_col,
-                      const int* __restrict__ skip_if, float* __restrict__ msums, int n_per_rank, int ranks) {
+                      const int* __restrict__ skip_if, float* __restrict__ msums_all, int n_per_rank, int ranks,
+                      int msum_slots) {
   if (skip_if != nullptr && __ldg(skip_if) != 0) return;
+  // the per-block sums are spread over msum_slots copies of [2][ranks] (the caller adds them up): thousands of
+  // blocks adding into one address serialise in L2 and cost more than the pass itself
+  float* msums = WSUM ? msums_all + (size_t)((blockIdx.y * gridDim.x + blockIdx.x) % msum_slots) * 2 * ranks : nullptr;
   __shared__ __align__(16) float cfac[1024];
   __shared__ __align__(16) float lcol[WSUM ? 1024 : 4];
   __shared__ float bacc[2][64];   // per-block sums by column owner (ranks <= 64)
@@ -352,7 +356,6 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
   // WSUM: this thread's 8 columns of segment s belong to rank r0[s] up to (excluding) element ks[s], to rank
   // r0[s] + 1 from there on (n_per_rank >= 8, so at most one boundary falls into a group)
   float acc_lo_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_lo_c[4] = {0.f, 0.f, 0.f, 0.f};
-  float acc_hi_r[4] = {0.f, 0.f, 0.f, 0.f}, acc_hi_c[4] = {0.f, 0.f, 0.f, 0.f};
   int r0[4] = {0, 0, 0, 0}, ks[4] = {8, 8, 8, 8};
   if (WSUM) {
 #pragma unroll
@@ -368,12 +371,18 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
     const float lr = (i < m_rows) ? __ldg(lse2_row + i) : CUDART_INF_F;
     const int jd = i + label_offset;   // column of this row's positive
     uint16_t* row = emat + (size_t)i * ld;
+    uint4 vin[4];   // all four loads of the row are in flight before any of its arithmetic starts
+#pragma unroll
+    for (int seg = 0; seg < 4; ++seg) {
+      const int j = col0 + seg * 256 + lane * 8;
+      vin[seg] = (j < n_pad) ? __ldcs(reinterpret_cast<const uint4*>(row + j)) : make_uint4(0u, 0u, 0u, 0u);
+    }
 #pragma unroll
     for (int seg = 0; seg < 4; ++seg) {
       const int c = seg * 256 + lane * 8;
       const int j = col0 + c;
       if (j < n_pad) {
-      uint4 v = *reinterpret_cast<const uint4*>(row + j);
+      uint4 v = vin[seg];
       const float cw = __ldg(cw_row + (j >> 6));
       const float rf = w_row * ex2f(fminf(cw - lr, 120.f));
       const float4 f0 = *reinterpret_cast<const float4*>(cfac + c);
@@ -386,58 +395,81 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
         e[2 * k] = __uint_as_float(w[k] << 16);
         e[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
       }
-      // the positive of row i (at most one per thread-row): exact probabilities from diag2 replace the entry
+#pragma unroll
+      for (int k = 0; k < 8; ++k) g[k] = e[k] * (rf + cf[k]);
+      v.x = pack_bf16x2(g[0], g[1]);
+      v.y = pack_bf16x2(g[2], g[3]);
+      v.z = pack_bf16x2(g[4], g[5]);
+      v.w = pack_bf16x2(g[6], g[7]);
+      // the positive of row i (at most one per thread-row, so this branch is rare): exact probabilities from diag2
+      // replace the rescaled entry -- patched into the packed words and taken out of the sums by correction, which
+      // keeps the per-element loops free of selects (and every array in registers)
       const bool diag_here = (jd >= j && jd < j + 8 && i < m_rows);
-      const int kd = diag_here ? jd - j : -1;
-      float gd = 0.f, trd = 0.f, tcd = 0.f;
+      float trd = 0.f, tcd = 0.f, ed = 0.f, cfd = 0.f, dfd = 0.f;
+      int kd = -1;
       if (diag_here) {
+        kd = jd - j;
         const float dg = __ldg(diag2 + i);
         const float lpr = dg - lr, lpc = dg - __ldg(lse2_col + jd);
         const float pr = w_row * ex2f(lpr), pc = w_col * ex2f(lpc);
-        gd = pr + pc - wsum;
         trd = pr * lpr;
         tcd = pc * lpc;
-      }
+        const uint32_t g16 = pack_bf16x2(pr + pc - wsum, 0.f) & 0xffffu;
+        const int wd = kd >> 1;
+        const uint32_t keep = (kd & 1) ? 0x0000ffffu : 0xffff0000u;
+        const uint32_t ins = (kd & 1) ? (g16 << 16) : g16;
+        v.x = (wd == 0) ? ((v.x & keep) | ins) : v.x;
+        v.y = (wd == 1) ? ((v.y & keep) | ins) : v.y;
+        v.z = (wd == 2) ? ((v.z & keep) | ins) : v.z;
+        v.w = (wd == 3) ? ((v.w & keep) | ins) : v.w;
+        if (WSUM) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = (k == kd) ? gd : e[k] * (rf + cf[k]);
+          for (int k = 0; k < 8; ++k) {
+            ed = (k == kd) ? e[k] : ed;
+            cfd = (k == kd) ? cf[k] : cfd;
+          }
+        }
+      }
       if (WSUM) {
         const float4 l0 = *reinterpret_cast<const float4*>(lcol + c);
         const float4 l1 = *reinterpret_cast<const float4*>(lcol + c + 4);
         const float df[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
-        // w * P * log2 P with t = e log2 e (0 for flushed / padded entries; the positive is taken out and added
-        // back exactly):   row: rf * (sum t + (c - lr) * sum e)        col: sum (cfac * t + dfac * e)
+        if (diag_here) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) dfd = (k == kd) ? df[k] : dfd;
+        }
+        // w * P * log2 P with t = e log2 e (0 for flushed / padded entries):
+        //   row: rf * (sum t + (c - lr) * sum e)        col: sum (cfac * t + dfac * e)
         const float dr = (rf > 0.f) ? cw - lr : 0.f;
+        const float td = ed * fmaxf(lg2f(ed), -200.f);     // the positive's recovered share, removed below
         if (ks[seg] == 8) {
           float st = 0.f, se = 0.f, sc = 0.f;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const float ek = (k == kd) ? 0.f : e[k];
-            const float t = ek * fmaxf(lg2f(ek), -200.f);
+            const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
             st += t;
-            se += ek;
+            se += e[k];
             sc = fmaf(cf[k], t, sc);
-            sc = fmaf(df[k], ek, sc);
+            sc = fmaf(df[k], e[k], sc);
           }
-          acc_lo_r[seg] += fmaf(rf, fmaf(dr, se, st), trd);
-          acc_lo_c[seg] += sc + tcd;
+          acc_lo_r[seg] += fmaf(rf, fmaf(dr, se - ed, st - td), trd);
+          acc_lo_c[seg] += sc - fmaf(cfd, td, dfd * ed) + tcd;
         } else {   // a rank boundary inside these 8 columns (n not a multiple of 8): element by element
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
             const float tr = (k == kd) ? trd : rf * fmaf(e[k], dr, t);
             const float tc = (k == kd) ? tcd : fmaf(cf[k], t, df[k] * e[k]);
-            const bool lo = k < ks[seg];
-            acc_lo_r[seg] += lo ? tr : 0.f;
-            acc_lo_c[seg] += lo ? tc : 0.f;
-            acc_hi_r[seg] += lo ? 0.f : tr;
-            acc_hi_c[seg] += lo ? 0.f : tc;
+            if (k < ks[seg]) {
+              acc_lo_r[seg] += tr;
+              acc_lo_c[seg] += tc;
+            } else if (r0[seg] + 1 < ranks) {   // next owner: straight into the block's table (rare path)
+              atomicAdd(&bacc[0][r0[seg] + 1], tr);
+              atomicAdd(&bacc[1][r0[seg] + 1], tc);
+            }
           }
         }
       }
-      v.x = pack_bf16x2(g[0], g[1]);
-      v.y = pack_bf16x2(g[2], g[3]);
-      v.z = pack_bf16x2(g[4], g[5]);
-      v.w = pack_bf16x2(g[6], g[7]);
       *reinterpret_cast<uint4*>(row + j) = v;
       }
     }
@@ -458,10 +490,6 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
       } else if (col0 + seg * 256 + lane * 8 < n_all) {   // a rank boundary inside the segment: lane by lane
         atomicAdd(&bacc[0][r0[seg]], acc_lo_r[seg]);
         atomicAdd(&bacc[1][r0[seg]], acc_lo_c[seg]);
-        if (ks[seg] < 8 && r0[seg] + 1 < ranks) {
-          atomicAdd(&bacc[0][r0[seg] + 1], acc_hi_r[seg]);
-          atomicAdd(&bacc[1][r0[seg] + 1], acc_hi_c[seg]);
-        }
       }
       }
     }

@@ -769,10 +769,11 @@ int mrclip_clip_gwrite_if(const void* a_rows, const void* b_all, mrclip_shape sh
 
 int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
                           const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
-                          float* msums, int n_per_rank, int ranks, void* stream) {
+                          float* msums, int msum_slots, int n_per_rank, int ranks, void* stream) {
   if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
   if (!emat || !lse2_row || !lse2_col || !diag2) return fail(-1, "emat_transform: NULL argument");
   if (msums && skip_if && !scale) return fail(-1, "emat_transform: scale is needed for the fallback sums");
+  if (msums && msum_slots <= 0) return fail(-1, "emat_transform: msum_slots must be positive");
   if (msums && (ranks > 64 || (ranks > 1 && n_per_rank < 8)))
     return fail(-1, "emat_transform: split sums need ranks <= 64 and n_per_rank >= 8 (got %d x %d)", ranks, n_per_rank);
   if (msums && (n_per_rank <= 0 || ranks <= 0 || (long)n_per_rank * ranks != sh.n_cols))
@@ -783,10 +784,11 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
   dim3 grid(ceil_div(f.n_pad, 1024), f.bands);
   cudaStream_t st = (cudaStream_t)stream;
   if (msums) {
-    CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks, st));
+    CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks * msum_slots, st));
     emat_transform_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
                                                       f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
-                                                      sh.label_offset, w_row, w_col, skip_if, msums, n_per_rank, ranks);
+                                                      sh.label_offset, w_row, w_col, skip_if, msums, n_per_rank, ranks,
+                                                      msum_slots);
     if (skip_if) {   // guard raised: the sums come from the exact recompute's partials instead
       const int items = f.num_rb * f.total_chunks;
       emat_fallback_sums_kernel<<<ceil_div(items, 256), 256, 0, st>>>(
@@ -797,7 +799,7 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
   } else {
     emat_transform_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
                                                        f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
-                                                       sh.label_offset, w_row, w_col, skip_if, nullptr, 1, 1);
+                                                       sh.label_offset, w_row, w_col, skip_if, nullptr, 1, 1, 1);
   }
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());

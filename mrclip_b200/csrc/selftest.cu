@@ -324,7 +324,7 @@ static void check_clip(int N, int D, int W, float s, float corr) {
                                flag, 0));
       CK(cudaMemset(dscale + r, 0, 4));
       MR(mrclip_emat_transform(sh, d.ws, emat, lse2_row_all + r * n, lse2_col_all, diag2 + r * n, d.scale, 1.f, 1.f, flag,
-                               msums + 2 * W * r, n, W, 0));
+                               msums + 2 * W * r, 1, n, W, 0));
       MR(mrclip_gmat_gemm_dot(0, emat, sh, d.Tbf, d.ld, (float)coef, d.scale, d.gout, d.ws, dA + (size_t)r * n * D,
                               MRCLIP_DT_F32, D, ai, dscale + r, 0));
       MR(mrclip_gmat_gemm(1, emat, sh, ai, d.ld, (float)coef, d.scale, d.gout, d.ws, dTp, MRCLIP_DT_F32, D, 0));
@@ -548,7 +548,7 @@ static void time_shape(int N, int D, int reps) {
     float ta = 0, tb = 0, tc = 0;
     const int* flag = mrclip_emat_flag(sh, d.ws);
     float* msums;
-    CK(cudaMalloc(&msums, 8));
+    CK(cudaMalloc(&msums, 64 * 8));
     const bool wsum_on = getenv("SELFTEST_NO_WSUM") == nullptr;
     for (int it = 0; it < reps + 2; ++it) {
       CK(cudaEventRecord(g0));
@@ -559,7 +559,7 @@ static void time_shape(int N, int D, int reps) {
       CK(cudaEventRecord(g1));
       MR(mrclip_emat_check(sh, d.ws, lse2_row, lse2_col, 0));
       MR(mrclip_clip_gwrite_if(d.Ibf, d.Tbf, sh, d.ld, lse2_row, lse2_col, d.scale, 1.f, 1.f, d.ws, emat, flag, 0));
-      MR(mrclip_emat_transform(sh, d.ws, emat, lse2_row, lse2_col, diag2, d.scale, 1.f, 1.f, flag, wsum_on ? msums : nullptr, N, 1, 0));
+      MR(mrclip_emat_transform(sh, d.ws, emat, lse2_row, lse2_col, diag2, d.scale, 1.f, 1.f, flag, wsum_on ? msums : nullptr, 64, N, 1, 0));
       CK(cudaEventRecord(g2));
       MR(mrclip_gmat_gemm_dot(0, emat, sh, d.Tbf, d.ld, 0.5f / N, d.scale, d.gout, d.ws, dA, MRCLIP_DT_F32, D, d.Ibf,
                               dscale, 0));

@@ -137,7 +137,8 @@ class CudaEngine:
                      msums=None, n_per_rank=0, ranks=1):
         """E -> G in place.  The guard decides on the device between the one-pass rewrite (normal) and the exact
         recompute of G (when a flushed E entry could carry gradient); exactly one of the two kernels does work.
-        msums (float32 [2, ranks], optional) receives the d_logit_scale sums split by column owner."""
+        msums (float32 [slots, 2, ranks], optional) receives the d_logit_scale sums split by column owner, spread
+        over `slots` copies that the caller adds up (msums.sum(0))."""
         st = self._stream()
         _cabi.check(self.lib.mrclip_emat_check(shape, ws.data_ptr(), lse2_row.data_ptr(), lse2_col.data_ptr(), st))
         flag = self.lib.mrclip_emat_flag(shape, ws.data_ptr())
@@ -146,7 +147,8 @@ class CudaEngine:
                                                    w_row, w_col, ws.data_ptr(), emat.data_ptr(), flag, st))
         _cabi.check(self.lib.mrclip_emat_transform(shape, ws.data_ptr(), emat.data_ptr(), lse2_row.data_ptr(),
                                                    lse2_col.data_ptr(), diag2.data_ptr(), scale.data_ptr(), w_row,
-                                                   w_col, flag, _ptr(msums), n_per_rank, ranks, st))
+                                                   w_col, flag, _ptr(msums), 1 if msums is None else msums.shape[0],
+                                                   n_per_rank, ranks, st))
 
     def gmat_gemm_dot(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out, dot_feat, dot_out):
         """gmat_gemm that also accumulates <d_out, dot_feat>/scale into dot_out (= d loss / d logit_scale)."""

@@ -143,7 +143,7 @@ class _Workspace:
         self.gmat = None
         self.dt_partial = None
         self.push = None
-        self.msums = torch.zeros((2, world), dtype=f32, device=device)
+        self.msums = torch.zeros((64, 2, world), dtype=f32, device=device)   # 64 slots against atomic contention
         self.has_emat = False
 
     def gmat_buffer(self, eng):
@@ -425,7 +425,8 @@ class _ClipLossFn(torch.autograd.Function):
             else:
                 colsum = work_cs = None
                 if need_s:   # column-softmax entropies of my columns live on every rank: W-float all-reduce, async
-                    colsum = ws.msums[1].clone()
+                    ms = ws.msums.sum(0)
+                    colsum = ms[1].clone()
                     work_cs = dist.all_reduce(colsum, op=dist.ReduceOp.SUM, async_op=True)
                 # text gradient: every rank holds G_q^T . I_q for all N text rows; the owner sums them
                 finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt)
@@ -434,7 +435,7 @@ class _ClipLossFn(torch.autograd.Function):
                     # scale * dL_r/dscale = L_r + ln2/(2n) * (sum P log2 P over my rows, row softmax, all columns
                     #                                         + over my columns, column softmax, all rows)
                     work_cs.wait()
-                    ent = ws.msums[0].sum() + colsum[rank]
+                    ent = ms[0].sum() + colsum[rank]
                     ds = ((gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ent)).reshape(1)
                     if not module.local_loss:
                         dist.all_reduce(ds, op=dist.ReduceOp.SUM)

@@ -218,7 +218,9 @@ class StandInEngine:
         g[idx, idx + shape.label_offset] -= (w_row + w_col)
         self._gview(emat, shape).copy_(g.to(torch.bfloat16))
         if msums is not None:
-            assert n_per_rank * ranks == shape.n_cols and tuple(msums.shape) == (2, ranks)
+            assert n_per_rank * ranks == shape.n_cols and tuple(msums.shape[1:]) == (2, ranks)
+            msums.zero_()
+            msums = msums[0]
             lp_row = t2 - lse2_row[:shape.m_rows].double()[:, None]
             lp_col = t2 - lse2_col[:shape.n_cols].double()[None, :]
             for r in range(ranks):

@@ -98,7 +98,7 @@ class EmulatedRanks:
             # production order per rank: forward keeps E, the rescale pass turns it into G, two plain GEMMs; the
             # text gradient is the sum over ranks of the [N, d] partials (NCCL reduce-scatter in production)
             dt_sum = torch.zeros((N, self.d), dtype=torch.float32, device=dev)
-            msums = torch.zeros((W, 2, W), dtype=torch.float32, device=dev)
+            msums = torch.zeros((W, 16, 2, W), dtype=torch.float32, device=dev)   # [rank][slot][direction][owner]
             for r in range(W):
                 rows, sh = self.rows(r), self.shape(r)
                 eng.clip_fwd_tiles_e(self.img_all[rows], self.txt_all, sh, s, 0, N, self.ws, gmat)
@@ -112,6 +112,7 @@ class EmulatedRanks:
                 dt_sum += part
                 out.append(dict(d_image=d_i.cpu().numpy(), dot=float(dot)))
             # scale * dL_r/dscale = L_r + ln2/(2n) * (negative entropies of my rows + of my columns)
+            msums = msums.sum(1)
             ds_r = [grad_output / scale * (float(losses[r]) + 0.6931471805599453 * 0.5 / n *
                                            float(msums[r, 0].sum() + msums[:, 1, r].sum())) for r in range(W)]
             for r in range(W):
@@ -471,3 +472,74 @@ def test_gemm_direct_epilogue(N, D, W, monkeypatch):
             assert rel_err(out[r]["d_image"], ref[r]["d_image"]) <= GRAD_TOL
             assert rel_err(out[r]["d_text"], ref[r]["d_text"]) <= GRAD_TOL
             assert abs(out[r]["d_scale"] - ref[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref[r]["d_logit_scale"]) + 1e-6
+
+
+@pytest.mark.parametrize("mode", [(False, True), (True, True)])
+def test_config2_gather_with_grad_w8(mode):
+    """BASELINE config 2: global batch 4096, dim 512, eight ranks, gather_with_grad -- every rank's loss, gradients
+    and d_scale against the float64 oracle (default backend, ranks emulated one after the other on this GPU)."""
+    from oracle.clip_oracle import clip_loss_oracle
+    N, D, W = 4096, 512, 8
+    img, txt = _features(N, D, 1234 + 2, corr=0.5)
+    n = N // W
+    parts = lambda x: [x[r * n:(r + 1) * n].numpy() for r in range(W)]
+    ref = clip_loss_oracle(parts(img), parts(txt), 14.285714, mode[0], mode[1])
+    out = EmulatedRanks(img, txt, W).clip(14.285714, mode[0], mode[1], backend="emat")
+    for r in range(W):
+        assert abs(out[r]["loss"] - ref[r]["loss"]) <= LOSS_TOL * abs(ref[r]["loss"])
+        assert rel_err(out[r]["d_image"], ref[r]["d_image"]) <= GRAD_TOL
+        assert rel_err(out[r]["d_text"], ref[r]["d_text"]) <= GRAD_TOL
+        assert abs(out[r]["d_scale"] - ref[r]["d_logit_scale"]) <= GRAD_TOL * abs(ref[r]["d_logit_scale"]) + 1e-7
+
+
+def test_config4_siglip_with_bias_full_size():
+    """BASELINE config 4 on one GPU: SigLipLoss, global batch 16384, dim 768, logit_bias, through the public module,
+    against fp32 torch on the same GPU (the reference's formula, loss.py:342-363)."""
+    from mrclip_b200 import SigLipLoss
+    dev = torch.device("cuda:0")
+    N, D = 16384, 768
+    img, txt = _features(N, D, 1234 + 4)
+    img, txt = img.to(dev), txt.to(dev)
+    i = img.clone().requires_grad_(True)
+    t = txt.clone().requires_grad_(True)
+    s = torch.tensor(10.0, device=dev, requires_grad=True)
+    b = torch.tensor(-10.0, device=dev, requires_grad=True)
+    loss = SigLipLoss()(i, t, s, b)
+    loss.backward()
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        i2 = img.clone().requires_grad_(True)
+        t2 = txt.clone().requires_grad_(True)
+        s2 = torch.tensor(10.0, device=dev, requires_grad=True)
+        b2 = torch.tensor(-10.0, device=dev, requires_grad=True)
+        logits = s2 * i2 @ t2.T + b2
+        labels = 2 * torch.eye(N, device=dev) - 1
+        ref = -torch.nn.functional.logsigmoid(labels * logits).sum() / N
+        ref.backward()
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    assert abs(loss.item() - ref.item()) <= LOSS_TOL * abs(ref.item())
+    assert rel_err(i.grad.cpu().numpy(), i2.grad.cpu().numpy()) <= GRAD_TOL
+    assert rel_err(t.grad.cpu().numpy(), t2.grad.cpu().numpy()) <= GRAD_TOL
+    assert abs(s.grad.item() - s2.grad.item()) <= GRAD_TOL * abs(s2.grad.item())
+    assert abs(b.grad.item() - b2.grad.item()) <= GRAD_TOL * abs(b2.grad.item())
+
+
+def test_fp32_features_amp_contract():
+    """Under AMP the reference hands fp32 features to the loss; gradients come back in fp32."""
+    from mrclip_b200 import ClipLoss
+    from oracle.clip_oracle import clip_loss_oracle
+    dev = torch.device("cuda:0")
+    img, txt = _features(2048, 512, 321)
+    i = img.to(dev).requires_grad_(True)
+    t = txt.to(dev).requires_grad_(True)
+    s = torch.tensor(14.285714, device=dev, requires_grad=True)
+    loss = ClipLoss(cache_labels=True)(i, t, s, output_dict=True)["contrastive_loss"]
+    loss.backward()
+    assert i.grad.dtype == torch.float32 and t.grad.dtype == torch.float32
+    ref = clip_loss_oracle([img.numpy()], [txt.numpy()], 14.285714)[0]
+    assert abs(loss.item() - ref["loss"]) <= LOSS_TOL * abs(ref["loss"])
+    assert rel_err(i.grad.cpu().numpy(), ref["d_image"]) <= GRAD_TOL
+    assert rel_err(t.grad.cpu().numpy(), ref["d_text"]) <= GRAD_TOL
+    assert abs(s.grad.item() - ref["d_logit_scale"]) <= GRAD_TOL * abs(ref["d_logit_scale"])
