@@ -395,8 +395,14 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
         e[2 * k] = __uint_as_float(w[k] << 16);
         e[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
       }
+      const float2 rf2 = make_float2(rf, rf);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g[k] = e[k] * (rf + cf[k]);
+      for (int k = 0; k < 4; ++k) {   // packed fp32 pairs: g = e * (rf + cf)
+        const float2 gg = fmul2(make_float2(e[2 * k], e[2 * k + 1]),
+                                fadd2(rf2, make_float2(cf[2 * k], cf[2 * k + 1])));
+        g[2 * k] = gg.x;
+        g[2 * k + 1] = gg.y;
+      }
       v.x = pack_bf16x2(g[0], g[1]);
       v.y = pack_bf16x2(g[2], g[3]);
       v.z = pack_bf16x2(g[4], g[5]);
@@ -443,15 +449,18 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
         const float dr = (rf > 0.f) ? cw - lr : 0.f;
         const float td = ed * fmaxf(lg2f(ed), -200.f);     // the positive's recovered share, removed below
         if (ks[seg] == 8) {
-          float st = 0.f, se = 0.f, sc = 0.f;
+          float2 st2 = make_float2(0.f, 0.f), se2 = st2, sc2 = st2;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const float t = e[k] * fmaxf(lg2f(e[k]), -200.f);
-            st += t;
-            se += e[k];
-            sc = fmaf(cf[k], t, sc);
-            sc = fmaf(df[k], e[k], sc);
+          for (int k = 0; k < 4; ++k) {   // packed fp32 pairs (FMUL2 / FADD2 / FFMA2)
+            const float2 e2 = make_float2(e[2 * k], e[2 * k + 1]);
+            const float2 l2 = make_float2(fmaxf(lg2f(e2.x), -200.f), fmaxf(lg2f(e2.y), -200.f));
+            const float2 t2 = fmul2(e2, l2);
+            st2 = fadd2(st2, t2);
+            se2 = fadd2(se2, e2);
+            sc2 = ffma2(make_float2(cf[2 * k], cf[2 * k + 1]), t2, sc2);
+            sc2 = ffma2(make_float2(df[2 * k], df[2 * k + 1]), e2, sc2);
           }
+          const float st = st2.x + st2.y, se = se2.x + se2.y, sc = sc2.x + sc2.y;
           acc_lo_r[seg] += fmaf(rf, fmaf(dr, se - ed, st - td), trd);
           acc_lo_c[seg] += sc - fmaf(cfd, td, dfd * ed) + tcd;
         } else {   // a rank boundary inside these 8 columns (n not a multiple of 8): element by element
