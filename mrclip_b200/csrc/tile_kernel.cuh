@@ -485,14 +485,14 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                      make_float4(v[hf * 32 + ck * 4], v[hf * 32 + ck * 4 + 1], v[hf * 32 + ck * 4 + 2],
                                  v[hf * 32 + ck * 4 + 3]));
             __syncwarp();
-            float acc = 0.f;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: the 32 loads stay in flight together
 #pragma unroll
             for (int r8 = 0; r8 < 8; ++r8) {
               const uint32_t base = stg + r8 * 128 + ((((lane >> 2) ^ r8)) << 4) + (lane & 3) * 4;
 #pragma unroll
-              for (int r = 0; r < 4; ++r) acc += __uint_as_float(lds_u32(base + r * 1024));
+              for (int r = 0; r < 4; ++r) acc[r] += __uint_as_float(lds_u32(base + r * 1024));
             }
-            cs[hf] = acc;
+            cs[hf] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
           }
           store_e(v);   // bf16 E through the same staging tile (its __syncwarp orders it after the column reads)
           const int band = rb * 4 + q;
