@@ -127,8 +127,7 @@ class _Workspace:
         if world > 1 and torch.device(device).type == "cuda" and os.environ.get("MRCLIP_AG", "push").lower() != "nccl":
             self.sym = _symmetric_buffers(self, device)
         self.flip = 0
-        self.img_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
-        self.txt_t = torch.zeros((self.ld, self.npad), dtype=bf, device=device)
+        self.img_t = self.txt_t = None      # [ld, npad] transposes, fused backend only (allocated on first use)
         self.scratch = torch.empty(max(int(eng.workspace_bytes(n, self.N, d)), 256), dtype=torch.uint8, device=device)
         # statistics in log2 units
         self.stats_local = torch.zeros((3, self.N), dtype=f32, device=device)      # col_m, col_l, (row lse2 in [:n])
@@ -208,9 +207,9 @@ def _backend(eng, ws):
 
 
 def _use_gmat(eng, ws):
-    """Backward backend: 'gmat' writes G = dLoss/dS once (bf16, n x N) and runs plain GEMMs (4-5 GEMM units
-    per step); 'fused' keeps O(N*D) memory but recomputes S per 384-wide slice of D (7 units).  MRCLIP_BWD
-    = gmat | fused | auto (default: gmat while the block stays under MRCLIP_GMAT_MAX_GIB, 16 GiB)."""
+    """True for the backends that contract a materialised bf16 G block with plain GEMMs ('emat': the block comes
+    from the forward's exponentials, 3 GEMM units per step; 'gmat': from a recompute pass, 4-5); 'fused' keeps
+    O(N*D) memory but recomputes S per 384-wide slice of D (7 units)."""
     return _backend(eng, ws) in ("gmat", "emat")
 
 
@@ -293,6 +292,9 @@ def _all_gather_rows(buf, rows):
 
 
 def _ensure_transposed(eng, ws):
+    if ws.img_t is None:
+        ws.img_t = torch.zeros((ws.ld, ws.npad), dtype=torch.bfloat16, device=ws.img_all.device)
+        ws.txt_t = torch.zeros((ws.ld, ws.npad), dtype=torch.bfloat16, device=ws.img_all.device)
     if not ws.transposed:
         eng.transpose(ws.img_all, ws.img_t)
         eng.transpose(ws.txt_all, ws.txt_t)
