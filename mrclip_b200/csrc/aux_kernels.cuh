@@ -1,6 +1,7 @@
-// Small HBM-bound helper kernels around the tile kernel: packing features to bf16, the
-// [N,D] -> [D,N] transpose that gives the second GEMM a K-major operand, and the reductions
-// that turn per-tile partials into LSE vectors, losses and gradients.
+// HBM-bound helper kernels around the tile and GEMM kernels: packing features to bf16, the
+// reductions that turn per-tile partials into LSE vectors, losses and gradients, the E -> G
+// rescale pass of the emat backend with its guard, the peer-store copy and slot sum of the
+// NVLink collectives, and the [N,D] -> [D,N] transpose the fused backend needs.
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
@@ -558,11 +559,6 @@ __global__ void push_copy_kernel(const uint4* __restrict__ src, long n16, const 
   uint4* dst = reinterpret_cast<uint4*>(__ldg(dsts + k) + offset_bytes);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x)
     dst[i] = src[i];
-}
-
-__global__ void fill_kernel(float* __restrict__ p, long n, float v) {
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
-    p[i] = v;
 }
 
 }  // namespace mrclip

@@ -1,21 +1,28 @@
 // The tile kernel: a persistent, warp-specialised tcgen05 GEMM whose accumulators never leave
-// the SM.  One CTA per SM walks a list of work items; inside an item it streams 128x128 tiles
-// of  S = A * B^T  (A = this rank's 128-row block, B = a 128-row block of the other modality)
-// through TMEM and consumes them in registers:
+// the SM.  One CTA per SM walks a list of work items; inside an item it streams 128 x BN tiles
+// of  S = A * B^T  (A = this rank's 128-row block, B = BN rows of the other modality; BN = 256
+// for the S-only modes, 128 for the fused backward) through TMEM and consumes them in registers:
 //
-//   MODE_FWD : per-row / per-column online log-sum-exp partials (ClipLoss) or the summed
-//              softplus (SigLipLoss).  Nothing N x N is written anywhere.
-//   MODE_BWD : recomputes S, turns it into the gradient tile G (bf16, written to shared memory
-//              in the UMMA K-major swizzled layout) and immediately contracts it with B again:
-//              dA[128, DC] += G[128,128] * B[128 cols, DC]   (second tcgen05 GEMM, accumulator
-//              stationary in TMEM for the whole item).
+//   MODE_FWD  : per-row / per-column online log-sum-exp partials (ClipLoss) or the summed
+//               softplus (SigLipLoss).  Nothing N x N is written anywhere (inference / no-grad).
+//   MODE_FWDE : the training forward.  Same statistics, and the exponentials it evaluates anyway,
+//               E = 2^(S2 - c) (c = the 32 x 64 sub-tile reference), leave the SM as a bf16 block
+//               through a swizzled staging tile and a TMA store; the backward rescales that block
+//               into the gradient of the logits instead of recomputing S.  SigLIP stores
+//               G = sigmoid(z) - delta directly.
+//   MODE_GW   : recomputes S and writes the exact gradient tile G (bf16) -- the guard's fallback
+//               for the E block (a no-op launch otherwise) and the MRCLIP_BWD=gmat backend.
+//   MODE_BWD  : MRCLIP_BWD=fused.  Recomputes S, turns it into G (bf16, written to shared memory
+//               in the UMMA K-major swizzled layout) and immediately contracts it with B again:
+//               dA[128, DC] += G[128,128] * B[128 cols, DC]   (second tcgen05 GEMM, accumulator
+//               stationary in TMEM for the whole item).  O(N*D) memory, 7 GEMM units per step.
 //
 // Replaces, for the reference (src/open_clip/loss.py): the logits GEMMs :117-124, the two
 // F.cross_entropy calls :135-136 and their autograd graph; SigLipLoss._loss :354-363.
 //
-// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA
-// issuer, warps 2..9 = epilogue (two warps per TMEM lane quarter, each taking 64 of the 128
-// tile columns).
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer (warp-uniform
+// loop, one elected lane issues), warps 2..9 = epilogue (two warps per TMEM lane quarter, each
+// taking half of the tile's columns, 64 at a time).
 #pragma once
 #include "ptx.cuh"
 #include <cuda_bf16.h>
