@@ -517,10 +517,8 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
 // one row block x one column chunk) are attributed to the rank owning the chunk's first column.
 __global__ void emat_fallback_sums_kernel(const int* __restrict__ run_if, const float2* __restrict__ sc_part,
                                           int num_rb, int num_chunks, int chunk_cols, int n_per_rank, int ranks,
-                                          const float* __restrict__ scale, float* __restrict__ msums) {
+                                          float w_row, float w_col, float* __restrict__ msums) {
   if (__ldg(run_if) == 0) return;
-  (void)scale;
-  const float to_log2 = 1.f;
   const int item = blockIdx.x * blockDim.x + threadIdx.x;
   if (item >= num_rb * num_chunks) return;
   const int chunk = item / num_rb;
@@ -531,8 +529,8 @@ __global__ void emat_fallback_sums_kernel(const int* __restrict__ run_if, const 
     x += v.x;
     y += v.y;
   }
-  atomicAdd(msums + r, x * to_log2);
-  atomicAdd(msums + ranks + r, y * to_log2);
+  atomicAdd(msums + r, x * w_row);
+  atomicAdd(msums + ranks + r, y * w_col);
 }
 
 // out[r, c] = sum_k slots[k][r][c]  (the owner's side of the fused reduce-scatter: W partial slots -> gradient)

@@ -772,7 +772,7 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
                           float* msums, int msum_slots, int n_per_rank, int ranks, void* stream) {
   if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
   if (!emat || !lse2_row || !lse2_col || !diag2) return fail(-1, "emat_transform: NULL argument");
-  if (msums && skip_if && !scale) return fail(-1, "emat_transform: scale is needed for the fallback sums");
+  (void)scale;
   if (msums && msum_slots <= 0) return fail(-1, "emat_transform: msum_slots must be positive");
   if (msums && (ranks > 64 || (ranks > 1 && n_per_rank < 8)))
     return fail(-1, "emat_transform: split sums need ranks <= 64 and n_per_rank >= 8 (got %d x %d)", ranks, n_per_rank);
@@ -793,7 +793,7 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
       const int items = f.num_rb * f.total_chunks;
       emat_fallback_sums_kernel<<<ceil_div(items, 256), 256, 0, st>>>(
           skip_if, reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(ws) + w.sc_part), f.num_rb,
-          f.total_chunks, f.tiles_per_chunk * kSBN, n_per_rank, ranks, scale, msums);
+          f.total_chunks, f.tiles_per_chunk * kSBN, n_per_rank, ranks, w_row, w_col, msums);
       g_launches.fetch_add(1);
     }
   } else {

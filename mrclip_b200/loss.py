@@ -47,7 +47,7 @@ except ImportError:  # pragma: no cover
 from ._cabi import Shape
 from .engine import default_engine
 
-__all__ = ["ClipLoss", "SigLipLoss", "gather_features", "set_engine"]
+__all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features", "set_engine"]
 
 _engine_override = None
 
@@ -331,6 +331,34 @@ def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
     return finish
 
 
+def _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, keep_e, gather_images):
+    """Pack + gather, the row-block tiles (keeping the bf16 exponentials when keep_e) and the statistics exchange:
+    leaves lse2_row_all / lse2_col_all (every row / column of the global batch, log2 units) and diag2 in ws."""
+    n, N = ws.n, ws.N
+    rows = slice(rank * n, (rank + 1) * n)
+    _gather_packed(eng, ws, image_features, text_features, rank, world, gather_images=gather_images)
+    if keep_e:
+        eng.clip_fwd_tiles_e(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
+        ws.has_emat = True
+    else:
+        eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
+    col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
+    eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
+    if world > 1 and ws.sym is not None and N % 4 == 0:     # (16-byte granular peer stores)
+        _, shdl, sptrs = ws.sym["stats"]
+        ws.stats_all[rank].copy_(ws.stats_local)
+        eng.push_copy(ws.stats_all[rank], sptrs, rank * 3 * N * 4, rank)
+        shdl.barrier()
+    elif world > 1:
+        dist.all_gather_into_tensor(ws.stats_all.view(world * 3, N), ws.stats_local)
+    if world > 1:
+        eng.lse2_merge(ws.stats_all[0, 0], ws.stats_all[0, 1], world, 3 * N, N, ws.lse2_col_all)
+        ws.lse2_row_all[:N].view(world, n).copy_(ws.stats_all[:, 2, :n])
+    else:
+        eng.lse2_merge(col_m, col_l, 1, N, N, ws.lse2_col_all)
+        ws.lse2_row_all[:N].copy_(row_lse)
+
+
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, image_features, text_features, logit_scale, module):
@@ -349,28 +377,8 @@ class _ClipLossFn(torch.autograd.Function):
         split_g = world > 1 and module.local_loss and not module.gather_with_grad
         split_g = split_g or (world > 1 and (n < 8 or world > 64))   # limits of the per-owner entropy sums
         use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g
-        _gather_packed(eng, ws, image_features, text_features, rank, world,
-                       gather_images=not use_emat and any(ctx.needs_input_grad))
-        if use_emat:
-            eng.clip_fwd_tiles_e(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
-            ws.has_emat = True
-        else:
-            eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
-        col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
-        eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
-        if world > 1 and ws.sym is not None and N % 4 == 0:     # (16-byte granular peer stores)
-            _, shdl, sptrs = ws.sym["stats"]
-            ws.stats_all[rank].copy_(ws.stats_local)
-            eng.push_copy(ws.stats_all[rank], sptrs, rank * 3 * N * 4, rank)
-            shdl.barrier()
-        elif world > 1:
-            dist.all_gather_into_tensor(ws.stats_all.view(world * 3, N), ws.stats_local)
-        if world > 1:
-            eng.lse2_merge(ws.stats_all[0, 0], ws.stats_all[0, 1], world, 3 * N, N, ws.lse2_col_all)
-            ws.lse2_row_all[:N].view(world, n).copy_(ws.stats_all[:, 2, :n])
-        else:
-            eng.lse2_merge(col_m, col_l, 1, N, N, ws.lse2_col_all)
-            ws.lse2_row_all[:N].copy_(row_lse)
+        _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, use_emat,
+                     gather_images=not use_emat and any(ctx.needs_input_grad))
         loss = torch.empty((1,), dtype=torch.float32, device=device)
         eng.clip_loss(ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2, n, rank * n, loss)
         ctx.loss_local = loss.clone() if (world > 1 and not module.local_loss) else loss
@@ -532,6 +540,137 @@ class ClipLoss(nn.Module):
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         total_loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+
+class _MultiPositiveFn(torch.autograd.Function):
+    """MR-CLIP's multi-positive (SupCon Eq. 2) loss on the same tiles.
+
+    With P(i) the samples of the global batch that share sample i's label and c = |P(i)|:
+        loss_img = mean_i( lse_row_i - (1/c) sum_{j in P(i)} S_ij ),     loss_txt = the same along columns,
+        L = delta * loss_img + (1 - delta) * loss_txt                                  (reference loss.py:626-644, :745)
+    so the forward is the ClipLoss forward (row / column LSE) plus class means of the features, which are O(N*D):
+        (1/c) sum_{j in P(i)} S_ij = s * <I_i, mean_{P(i)} T>.
+    The gradient of the logits is  G = delta*Prow + (1-delta)*Pcol - [same label]/c  =  G_k + delta_ij - [same]/c with
+    G_k what the emat pipeline already builds for weights (delta, 1-delta); the difference is again a class mean:
+        dI_i = s/n * ( (G_k T)_i + T_i - mean_{P(i)} T ),      dT_j = s/n * ( (G_k^T I)_j + I_j - mean_{P(j)} I ).
+    Nothing N x N beyond the bf16 E block is ever formed (the reference builds two [n, N] fp32 logit matrices, the
+    [n, N] mask and their softmaxes)."""
+
+    @staticmethod
+    def forward(ctx, image_features, text_features, logit_scale, labels, delta, module):
+        eng = _engine()
+        _check_inputs(image_features, text_features)
+        device = image_features.device
+        n, d = image_features.shape
+        world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
+        if labels.dim() != 1 or labels.shape[0] != n:
+            raise ValueError(f"tokenized_texts must be one label per sample ([{n}]), got {tuple(labels.shape)}")
+        if world > 1 and not (module.local_loss and module.gather_with_grad):
+            # (the reference's mask is [n, N]: it only fits the logits with local_loss, loss.py:707-712)
+            raise NotImplementedError("MultiPositiveClipLoss on several ranks needs local_loss=True, gather_with_grad=True")
+        if world > 1 and (n < 8 or world > 64):
+            raise NotImplementedError("MultiPositiveClipLoss: per-rank batch must be >= 8 and world_size <= 64")
+        ws = module._pool.take(eng, device, n, world, d)
+        N = ws.N
+        scale = _scalar_f32(logit_scale, device)
+        shape = Shape(n, N, d, rank * n)
+        rows = slice(rank * n, (rank + 1) * n)
+        keep_e = any(ctx.needs_input_grad)
+        # the class means need every rank's rows of both modalities, and every rank's labels
+        _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, keep_e, gather_images=True)
+        labels = labels.detach().to(device=device, dtype=torch.long).contiguous()
+        if world > 1:
+            labels_all = torch.empty((N,), dtype=torch.long, device=device)
+            dist.all_gather_into_tensor(labels_all, labels)
+        else:
+            labels_all = labels
+        _, inv_all = torch.unique(labels_all, return_inverse=True)
+        cnt = torch.bincount(inv_all).to(torch.float32)
+        ncls = cnt.shape[0]
+        img_f, txt_f = ws.img_all.float(), ws.txt_all.float()          # the bf16 operands the kernels see
+        t_mean = torch.zeros((ncls, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, txt_f)
+        i_mean = torch.zeros((ncls, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, img_f)
+        t_mean /= cnt[:, None]
+        i_mean /= cnt[:, None]
+        inv_r = inv_all[rows]
+        corr_i = txt_f[rows] - t_mean[inv_r]         # T_i - mean_{P(i)} T      [n, ld]
+        corr_t = img_f[rows] - i_mean[inv_r]         # I_j - mean_{P(j)} I
+        pos_img = scale * (img_f[rows] * t_mean[inv_r]).sum(-1)        # (1/c) sum_{P(i)} S_ij
+        pos_txt = scale * (txt_f[rows] * i_mean[inv_r]).sum(-1)
+        ln2 = 0.6931471805599453
+        loss_img = (ws.lse2_row_all[rows] * ln2 - pos_img).mean()
+        loss_txt = (ws.lse2_col_all[rows] * ln2 - pos_txt).mean()
+        loss = (delta * loss_img + (1.0 - delta) * loss_txt).reshape(1)
+
+        ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+        ctx.scale, ctx.delta, ctx.loss_local = scale, float(delta), loss
+        ctx.corr = (corr_i, corr_t)
+        ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+        ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+        if not keep_e:
+            module._pool.give_back(ws)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        eng = _engine()
+        ws, module = ctx.ws, ctx.module
+        n, N, d, rank, world = ctx.shape_args
+        device = ws.img_all.device
+        rows = slice(rank * n, (rank + 1) * n)
+        shape = Shape(n, N, d, rank * n)
+        gout = grad_output.detach().reshape(1).to(torch.float32).contiguous()
+        coef, delta = 1.0 / n, ctx.delta
+        need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
+        d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
+        d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
+        gmat = ws.gmat_buffer(eng)
+        # G_k = delta*Prow + (1-delta)*Pcol - delta_ij  (exact positives); entropies weighted likewise
+        eng.emat_to_gmat(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2,
+                         ctx.scale, delta, 1.0 - delta, ws.scratch, gmat, ws.msums if need_s else None, n, world)
+        ms = ws.msums.sum(0) if need_s else None
+        if world == 1:
+            eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+            eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, ctx.scale, gout, ws.scratch, d_txt)
+            ent = ms.sum() if need_s else None
+        else:
+            colsum = work_cs = None
+            if need_s:
+                colsum = ms[1].clone()
+                work_cs = dist.all_reduce(colsum, op=dist.ReduceOp.SUM, async_op=True)
+            finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt)
+            eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+            ent = None
+            if need_s:
+                work_cs.wait()
+                ent = ms[0].sum() + colsum[rank]
+            finish_dt()
+        # class-mean corrections: + s/n * (T_i - mean_{P(i)} T)  and  + s/n * (I_j - mean_{P(j)} I)
+        k = (coef * gout * ctx.scale).to(torch.float32)
+        corr_i, corr_t = ctx.corr
+        d_img += (k * corr_i[:, :d]).to(d_img.dtype)
+        d_txt += (k * corr_t[:, :d]).to(d_txt.dtype)
+        d_scale = None
+        if need_s:
+            # scale * dL/dscale = L + ln2/n * (delta * sum Prow log2 Prow + (1-delta) * sum Pcol log2 Pcol)
+            ds = (gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * coef) * ent)
+            shp, dt = ctx.scale_meta
+            d_scale = ds.reshape(shp).to(dt)
+        module._pool.give_back(ws)
+        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None, None, None
+
+
+class MultiPositiveClipLoss(ClipLoss):
+    """Reference ``MultiPositiveClipLoss`` (loss.py:671-747): samples whose ``tokenized_texts`` label (MR-CLIP's binned
+    TE / TR / TI class, train.py:123) is equal are positives of each other.  Same constructor and call signature;
+    returns ``{"multi contrastive_loss": loss}`` with ``output_dict=True`` like the reference."""
+
+    def forward(self, image_features, text_features, logit_scale, delta=0.5, tokenized_texts=None, output_dict=False):
+        if tokenized_texts is None:
+            raise ValueError("MultiPositiveClipLoss needs tokenized_texts (one integer label per sample)")
+        total_loss = _MultiPositiveFn.apply(image_features, text_features, logit_scale, tokenized_texts, float(delta),
+                                            self)
+        return {"multi contrastive_loss": total_loss} if output_dict else total_loss
 
 
 class _SigLipLossFn(torch.autograd.Function):

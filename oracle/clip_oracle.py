@@ -24,6 +24,7 @@ __all__ = [
     "cross_entropy_mean",
     "clip_loss_oracle",
     "siglip_loss_oracle",
+    "multipositive_loss_oracle",
     "bf16_round",
 ]
 
@@ -176,4 +177,60 @@ def siglip_loss_oracle(image_parts, text_parts, logit_scale: float, logit_bias: 
                         d_logit_bias=grad_output * g_b))
     for r in range(W):
         out[r]["d_text"] = grad_output * d_text[r]
+    return out
+
+
+def multipositive_loss_oracle(image_parts, text_parts, label_parts, logit_scale: float, delta: float = 0.5,
+                              grad_output: float = 1.0):
+    """MR-CLIP's ``MultiPositiveClipLoss`` (loss.py:671-747 with ``multi_positive_cross_entropy_loss`` :626-644):
+    samples that share a label are positives of each other.
+
+    Per rank r (``local_loss=True, gather_with_grad=True`` when world_size > 1; plain when 1):
+        pos_mask = labels_r[:, None] == labels_all[None, :]                                  (:707-712)
+        loss_img = mean_i( -(pos_mask * log_softmax(s I_r T_all^T))_i.sum() / count_i )      (:626-644; the +1e-12 inside
+        loss_txt = the same on s T_r I_all^T with the same mask                               the log is below fp32 eps)
+        L_r = delta * loss_img + (1 - delta) * loss_txt                                      (:745)
+    Gradients follow the reference's autograd graph: the gathered copies carry gradient, and
+    ``torch.distributed.nn.all_gather``'s backward sums every rank's contribution (reduce-scatter).
+    Returns one dict per rank: loss, d_image, d_text, d_logit_scale.
+    """
+    W = len(image_parts)
+    I = [np.asarray(x, dtype=np.float64) for x in image_parts]
+    T = [np.asarray(x, dtype=np.float64) for x in text_parts]
+    L = [np.asarray(x).astype(np.int64) for x in label_parts]
+    I_all, T_all, L_all = np.concatenate(I), np.concatenate(T), np.concatenate(L)
+    n = I[0].shape[0]
+    s = float(logit_scale)
+    out = []
+    dI_all = np.zeros_like(I_all)
+    dT_all = np.zeros_like(T_all)
+    for r in range(W):
+        rows = slice(r * n, (r + 1) * n)
+        mask = (L[r][:, None] == L_all[None, :]).astype(np.float64)
+        cnt = np.maximum(mask.sum(axis=1), 1.0)
+        c_img = I[r] @ T_all.T          # [n, N]
+        c_txt = T[r] @ I_all.T
+        terms = []
+        loss = 0.0
+        ds = 0.0
+        for c, w in ((c_img, delta), (c_txt, 1.0 - delta)):
+            z = s * c
+            logp = z - _lse(z, 1)[:, None]
+            loss += w * float((-(mask * logp).sum(axis=1) / cnt).mean())
+            # d loss / d z = w/n * (softmax * (sum_j mask_ij / cnt_i) - mask / cnt) = w/n * (softmax - mask/cnt)
+            g = w / n * (np.exp(logp) - mask / cnt[:, None])
+            terms.append(g)
+            ds += float((g * c).sum())
+        g_img, g_txt = terms
+        # image-direction graph: I_r (local) x T_all (gathered, with grad)
+        dI_all[rows] += s * g_img @ T_all
+        dT_all += s * g_img.T @ I[r]
+        # text-direction graph: T_r (local) x I_all (gathered, with grad)
+        dT_all[rows] += s * g_txt @ I_all
+        dI_all += s * g_txt.T @ T[r]
+        out.append(dict(loss=loss, d_logit_scale=grad_output * ds))
+    for r in range(W):
+        rows = slice(r * n, (r + 1) * n)
+        out[r]["d_image"] = grad_output * dI_all[rows]
+        out[r]["d_text"] = grad_output * dT_all[rows]
     return out

@@ -42,6 +42,12 @@ def make_features(n_total: int, d: int, seed: int, corr: float):
     return img.bfloat16().float(), txt.bfloat16().float()
 
 
+def make_labels(n_total: int, classes: int, seed: int):
+    """class labels with repeats (the reference's binned TE/TR/TI classes, preprocessing.py:442-491)"""
+    g = torch.Generator().manual_seed(seed + 17)
+    return torch.randint(0, classes, (n_total,), generator=g, dtype=torch.int64)
+
+
 def _worker(rank, world, init_file, case, img, txt, ret):
     ref = load_reference()
     if world > 1:
@@ -51,7 +57,18 @@ def _worker(rank, world, init_file, case, img, txt, ret):
     t_loc = txt[rank * n:(rank + 1) * n].clone().requires_grad_(True)
     scale = torch.tensor(case["scale"], dtype=torch.float32, requires_grad=True)
     res = {}
-    if case["kind"] == "clip":
+    if case["kind"] == "mpos":
+        # MR-CLIP's MultiPositiveClipLoss (loss.py:671-747): samples that share the binned-metadata label are positives
+        lab_all = make_labels(case["n_total"], case["classes"], case["seed"])
+        lab = lab_all[rank * n:(rank + 1) * n].clone()
+        mod = ref.MultiPositiveClipLoss(local_loss=case["local_loss"], gather_with_grad=case["gather_with_grad"],
+                                        cache_labels=False, rank=rank, world_size=world)
+        out = mod(i_loc, t_loc, scale, delta=case["delta"], tokenized_texts=lab, output_dict=True)
+        assert list(out) == ["multi contrastive_loss"]
+        loss = out["multi contrastive_loss"]
+        res["labels_in"] = lab.numpy()
+        (loss * case["grad_output"]).backward()
+    elif case["kind"] == "clip":
         mod = ref.ClipLoss(local_loss=case["local_loss"], gather_with_grad=case["gather_with_grad"],
                            cache_labels=True, rank=rank, world_size=world)
         loss = mod(i_loc, t_loc, scale)
@@ -121,6 +138,14 @@ CASES += [
          local_loss=True, gather_with_grad=True, grad_output=1.0),
     dict(name="clip_w2_ragged", kind="clip", world=2, n_total=300, d=72, seed=9, corr=0.2, scale=30.0,
          local_loss=True, gather_with_grad=True, grad_output=1.0),
+    dict(name="mpos_w1", kind="mpos", world=1, n_total=64, d=32, seed=21, corr=0.3, scale=14.285714, classes=12,
+         delta=0.5, local_loss=False, gather_with_grad=False, grad_output=1.0),
+    dict(name="mpos_w1_delta03_ragged", kind="mpos", world=1, n_total=200, d=72, seed=22, corr=0.15, scale=30.0,
+         classes=23, delta=0.3, local_loss=False, gather_with_grad=False, grad_output=3.0),
+    dict(name="mpos_w2_ll1_gg1", kind="mpos", world=2, n_total=64, d=32, seed=23, corr=0.3, scale=14.285714,
+         classes=10, delta=0.5, local_loss=True, gather_with_grad=True, grad_output=1.0),
+    dict(name="mpos_w4_ll1_gg1", kind="mpos", world=4, n_total=128, d=64, seed=24, corr=0.3, scale=14.285714,
+         classes=9, delta=0.7, local_loss=True, gather_with_grad=True, grad_output=1.0),
     dict(name="siglip_w1", kind="siglip", world=1, n_total=64, d=32, seed=11, corr=0.3, scale=10.0, bias=-10.0,
          grad_output=1.0),
     dict(name="siglip_w4", kind="siglip", world=4, n_total=64, d=32, seed=12, corr=0.3, scale=10.0, bias=-10.0,
@@ -130,13 +155,15 @@ CASES += [
 ]
 
 
-def main():
+def main(only=None):
     if not os.path.exists(REF_LOSS):
         sys.exit(f"{REF_LOSS} not found: golden vectors can only be generated in the build container")
     os.makedirs(OUT_DIR, exist_ok=True)
     torch.manual_seed(0)
     torch.set_num_threads(4)
     for case in CASES:
+        if only and not case["name"].startswith(only):
+            continue
         out = run_case(case)
         path = os.path.join(OUT_DIR, case["name"] + ".npz")
         np.savez_compressed(path, **out)
@@ -144,4 +171,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(sys.argv[1] if len(sys.argv) > 1 else None)     # optional name prefix, e.g. "mpos"

@@ -15,7 +15,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from conftest import load_golden, rel_err  # noqa: E402
-from mrclip_b200 import ClipLoss, SigLipLoss  # noqa: E402
+from mrclip_b200 import ClipLoss, MultiPositiveClipLoss, SigLipLoss  # noqa: E402
 
 
 def main():
@@ -41,7 +41,15 @@ def main():
             t = torch.from_numpy(case["text"][rows]).to(dev).requires_grad_(True)
             s = torch.tensor(float(m["scale"]), device=dev, requires_grad=True)
             ref = case["ranks"][rank]
-            if m["kind"] == "clip":
+            if m["kind"] == "mpos":
+                if backend not in ("emat", "emat-nccl"):
+                    continue        # the multi-positive loss always runs the E-block pipeline
+                mod = MultiPositiveClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
+                                            rank=rank, world_size=world)
+                lab = torch.from_numpy(ref["labels_in"]).to(dev)
+                loss = mod(i, t, s, delta=float(m["delta"]), tokenized_texts=lab)
+                ok_labels = True
+            elif m["kind"] == "clip":
                 mod = ClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
                                cache_labels=True, rank=rank, world_size=world)
                 loss = mod(i, t, s)

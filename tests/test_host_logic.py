@@ -14,7 +14,7 @@ import torch.multiprocessing as mp
 
 import mrclip_b200
 from conftest import StandInEngine, golden_names, load_golden, rel_err
-from mrclip_b200 import ClipLoss, SigLipLoss
+from mrclip_b200 import ClipLoss, MultiPositiveClipLoss, SigLipLoss
 
 # stand-in math is float64 but features are packed to bf16 (exact for the fixtures) and grads are
 # returned in the input dtype (fp32)
@@ -73,6 +73,13 @@ def _run_rank(case, rank, world, img, txt):
         loss = res["contrastive_loss"]
         num_logits = n if (world > 1 and m["local_loss"]) else img.shape[0]
         out["labels"] = mod.get_ground_truth(i_loc.device, num_logits).numpy()
+    elif m["kind"] == "mpos":
+        mod = MultiPositiveClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
+                                    cache_labels=False, rank=rank, world_size=world)
+        res = mod(i_loc, t_loc, scale, delta=float(m["delta"]),
+                  tokenized_texts=torch.from_numpy(case["ranks"][rank]["labels_in"]), output_dict=True)
+        assert list(res) == ["multi contrastive_loss"]
+        loss = res["multi contrastive_loss"]
     else:
         bias = torch.tensor(float(m["bias"]), requires_grad=True)
         loss = SigLipLoss(rank=rank, world_size=world)(i_loc, t_loc, scale, bias)
@@ -91,7 +98,7 @@ def _compare(out, ref, kind, grad_tol=GRAD_TOL, scale_tol=1e-4):
     assert abs(out["d_scale"] - float(ref["d_scale"])) <= scale_tol * max(abs(float(ref["d_scale"])), 1e-3)
     if kind == "clip":
         assert np.array_equal(out["labels"], ref["labels"])
-    else:
+    elif kind == "siglip":
         assert abs(out["d_bias"] - float(ref["d_bias"])) <= 1e-4 * max(abs(float(ref["d_bias"])), 1e-3)
 
 
@@ -103,9 +110,13 @@ def test_single_rank_matches_reference(name, backend, standin_engine, monkeypatc
     out = _run_rank(case, 0, 1, case["image"], case["text"])
     # G is rounded to bf16 in the gmat / emat stand-in, as in the kernels
     # (emat, one rank: d_scale = <dI, I>/scale inherits the bf16 rounding of G, which a 16-row fixture does not average out)
-    _compare(out, case["ranks"][0], case["meta"]["kind"], grad_tol=GRAD_TOL if backend == "fused" else 5e-3,
+    bf16_g = backend != "fused" or case["meta"]["kind"] == "mpos"      # G rounded to bf16, as in the kernels
+    _compare(out, case["ranks"][0], case["meta"]["kind"], grad_tol=5e-3 if bf16_g else GRAD_TOL,
              scale_tol=1e-2 if backend == "emat" else 1e-4)
     used = set(standin_engine.calls)
+    if case["meta"]["kind"] == "mpos":      # always the E-block pipeline
+        assert {"clip_fwd_tiles_e", "emat_to_gmat", "gmat_gemm"} <= used
+        return
     assert ("gmat_gemm" in used) == (backend in ("gmat", "emat"))
     assert ("clip_bwd" in used or "siglip_bwd" in used) == (backend == "fused")
     assert ("clip_fwd_tiles_e" in used or "siglip_fwd_e" in used) == (backend == "emat")
@@ -153,13 +164,16 @@ def test_multi_rank_gloo_matches_reference(name):
     # every case runs the default (emat: reduce-scatter of the text-gradient partials); the older two
     # orchestrations alternate over the cases
     backends = ["emat", "gmat" if (MULTI.index(name) % 2 == 0) else "fused"]
+    if case["meta"]["kind"] == "mpos":
+        backends = ["emat"]          # the multi-positive loss has one pipeline
     mgr = mp.Manager()
     ret = mgr.dict()
     for backend in backends:
         with tempfile.TemporaryDirectory() as td:
             mp.spawn(_dist_worker, args=(world, os.path.join(td, "init"), name, backend, ret), nprocs=world, join=True)
         for r in range(world):
-            _compare(ret[r], case["ranks"][r], case["meta"]["kind"], grad_tol=GRAD_TOL if backend == "fused" else 5e-3)
+            bf16_g = backend != "fused" or case["meta"]["kind"] == "mpos"
+            _compare(ret[r], case["ranks"][r], case["meta"]["kind"], grad_tol=5e-3 if bf16_g else GRAD_TOL)
 
 
 def _gather_worker(rank, world, init_file, ret):

@@ -9,7 +9,7 @@ import pytest
 
 from conftest import golden_names, load_golden, rel_err
 from oracle.clip_oracle import (bf16_round, clip_loss_oracle, cross_entropy_mean, ground_truth_labels,
-                                siglip_loss_oracle)
+                                multipositive_loss_oracle, siglip_loss_oracle)
 
 LOSS_TOL = 2e-6      # fp32 reference vs float64 oracle
 GRAD_TOL = 2e-5
@@ -97,7 +97,7 @@ def test_cross_entropy_and_bf16_round():
     assert np.array_equal(bf16_round(x), torch.from_numpy(x).bfloat16().float().numpy())
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if "_w1" in n])
+@pytest.mark.parametrize("name", [n for n in golden_names() if "_w1" in n and not n.startswith("mpos")])
 def test_timed_port_matches_reference(name):
     """oracle/clip_port.py (the CPU baseline bench.py times) reproduces the reference's W=1 outputs."""
     import torch
@@ -129,3 +129,19 @@ def test_timed_port_rank_block_matches_oracle():
         loss, di, dt, ds = clip_rank_step(ti[rows], tt[rows], ti, tt, 10.0, r * n)
         assert abs(loss.item() - ref[r]["loss"]) < 1e-5
         assert rel_err(di.numpy(), ref[r]["d_image"]) < 1e-5 and rel_err(dt.numpy(), ref[r]["d_text"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", golden_names("mpos_"))
+def test_multipositive_oracle_matches_reference(name):
+    """the reference's MultiPositiveClipLoss (loss.py:671-747), single process and gloo groups of 2 / 4"""
+    g = load_golden(name)
+    m, W = g["meta"], g["world"]
+    labels = [g["ranks"][r]["labels_in"] for r in range(W)]
+    out = multipositive_loss_oracle(_parts(g["image"], W), _parts(g["text"], W), labels, m["scale"], m["delta"],
+                                    float(m["grad_output"]))
+    for r in range(W):
+        ref = g["ranks"][r]
+        assert abs(out[r]["loss"] - float(ref["loss"])) <= LOSS_TOL * max(1.0, abs(float(ref["loss"])))
+        assert rel_err(out[r]["d_image"], ref["d_image"]) <= GRAD_TOL
+        assert rel_err(out[r]["d_text"], ref["d_text"]) <= GRAD_TOL
+        assert abs(out[r]["d_logit_scale"] - float(ref["d_scale"])) <= 5e-5 * max(abs(float(ref["d_scale"])), 1e-3)
