@@ -584,12 +584,18 @@ class _MultiPositiveFn(torch.autograd.Function):
             dist.all_gather_into_tensor(labels_all, labels)
         else:
             labels_all = labels
-        _, inv_all = torch.unique(labels_all, return_inverse=True)
-        cnt = torch.bincount(inv_all).to(torch.float32)
-        ncls = cnt.shape[0]
+        # dense class ids in [0, N) without a data-dependent shape (torch.unique would synchronise the host):
+        # sort, flag the first sample of every class, prefix-sum the flags, scatter back
+        sorted_l, order = torch.sort(labels_all)
+        first = torch.ones_like(sorted_l)
+        first[1:] = (sorted_l[1:] != sorted_l[:-1]).to(sorted_l.dtype)
+        inv_all = torch.empty_like(sorted_l)
+        inv_all[order] = torch.cumsum(first, 0) - 1
+        cnt = torch.zeros((N,), dtype=torch.float32, device=device).index_add_(
+            0, inv_all, torch.ones((N,), dtype=torch.float32, device=device)).clamp_(min=1.0)
         img_f, txt_f = ws.img_all.float(), ws.txt_all.float()          # the bf16 operands the kernels see
-        t_mean = torch.zeros((ncls, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, txt_f)
-        i_mean = torch.zeros((ncls, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, img_f)
+        t_mean = torch.zeros((N, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, txt_f)
+        i_mean = torch.zeros((N, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, img_f)
         t_mean /= cnt[:, None]
         i_mean /= cnt[:, None]
         inv_r = inv_all[rows]
