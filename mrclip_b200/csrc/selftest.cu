@@ -244,7 +244,6 @@ static void check_clip(int N, int D, int W, float s, float corr) {
   for (int r = 0; r < W; ++r) {
     mrclip_shape sh = {n, N, D, r * n};
     const char* ai = (const char*)d.Ibf + (size_t)r * n * d.ld * 2;
-    const char* at = (const char*)d.Tbf + (size_t)r * n * d.ld * 2;
     MR(mrclip_clip_bwd(ai, d.Tbf, d.Tt, d.npad, sh, d.ld, lse2_row_all + r * n, lse2_col_all, d.scale, 1.f, 1.f,
                        (float)coef, d.gout, d.ws, dA + (size_t)r * n * D, MRCLIP_DT_F32, D, dscale + r, 0, 0));
     CK(cudaDeviceSynchronize());
