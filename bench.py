@@ -38,10 +38,18 @@ def parse():
     ap.add_argument("--feature-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="clip", choices=["clip", "siglip", "mpos"],
+                    help="clip = the headline (BASELINE configs[2]); siglip / mpos: extra measurements of the other two "
+                         "losses on the same shapes (not the headline metric)")
     return ap.parse_args()
 
 
 def workload_name(args):
+    if getattr(args, "workload", "clip") == "siglip":
+        return f"SigLipLoss with logit_bias, global batch {args.global_batch}, dim {args.dim} (extra; cf. BASELINE.json configs[3])"
+    if getattr(args, "workload", "clip") == "mpos":
+        return (f"MultiPositiveClipLoss local_loss=True gather_with_grad=True delta=0.5, {max(args.global_batch // 16, 1)} "
+                f"label classes, global batch {args.global_batch}, dim {args.dim} (extra; SURVEY 8f N1)")
     return (f"ClipLoss local_loss=True gather_with_grad=True, global batch {args.global_batch}, dim {args.dim} "
             f"(BASELINE.json configs[2])")
 
@@ -128,7 +136,7 @@ class ClockSampler:
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from mrclip_b200 import ClipLoss
+    from mrclip_b200 import ClipLoss, MultiPositiveClipLoss, SigLipLoss
     from mrclip_b200.engine import default_engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -159,11 +167,26 @@ def run_ours(args):
     img_d = img_h.to(dev).requires_grad_(True)
     txt_d = txt_h.to(dev).requires_grad_(True)
     scale = torch.tensor(LOGIT_SCALE, device=dev, requires_grad=True)
-    loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+    if args.workload == "siglip":
+        loss_mod = SigLipLoss(rank=rank, world_size=world)
+        scale = torch.tensor(10.0, device=dev, requires_grad=True)
+        bias = torch.tensor(-10.0, device=dev, requires_grad=True)
+    elif args.workload == "mpos":
+        loss_mod = MultiPositiveClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+        lab_all = torch.randint(0, max(N // 16, 1), (N,), generator=torch.Generator().manual_seed(99))
+        labels_d = lab_all[rows].to(dev)
+    else:
+        loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
 
     def step(i, t):
         i.grad = t.grad = scale.grad = None
-        loss = loss_mod(i, t, scale)
+        if args.workload == "siglip":
+            bias.grad = None
+            loss = loss_mod(i, t, scale, bias)
+        elif args.workload == "mpos":
+            loss = loss_mod(i, t, scale, delta=0.5, tokenized_texts=labels_d)
+        else:
+            loss = loss_mod(i, t, scale)
         loss.backward()
         return loss
 
@@ -202,12 +225,14 @@ def run_ours(args):
     # launching stream; the roofline is quoted for the costliest op that carries algorithmic flops
     ALG_OPS = {"clip_fwd_tiles": "tile_kernel<MODE_FWD> (S = A.B^T tiles + online LSE, 2nND flop)",
                "clip_fwd_tiles_e": "tile_kernel<MODE_FWDE> (S = A.B^T tiles + online LSE + bf16 E block out, 2nND flop)",
+               "siglip_fwd_e": "tile_kernel<MODE_FWDE, SIGLIP> (S tiles + softplus sum + bf16 G block out, 2nND flop)",
                "gmat_gemm": "gemm2_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
                "gmat_gemm_dot": "gemm2_kernel (dA = G.B from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
                "gmat_gemm_push": "gemm2_kernel<PUSH> (dB partial = G^T.A, tiles pushed to their owner over NVLink, 2nND flop)",
                "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)"}
-    TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "clip_fwd_reduce", "lse2_merge", "clip_loss",
-             "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "gmat_gemm_push", "sum_slots", "clip_bwd"]
+    TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "siglip_fwd_e", "clip_fwd_reduce", "lse2_merge",
+             "clip_loss", "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "gmat_gemm_push", "push_copy",
+             "sum_slots", "clip_bwd"]
     ev = {k: [] for k in TIMED}
     originals = {k: getattr(eng, k) for k in TIMED}
 
@@ -306,7 +331,7 @@ def run_ours(args):
             traffic = json.load(open(tp)).get(dom)
         ws_mb = eng.workspace_bytes(n, N, D) / 2 ** 20
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": METRIC if args.workload == "clip" else METRIC.replace("ClipLoss", {"siglip": "SigLipLoss", "mpos": "MultiPositiveClipLoss"}[args.workload]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": N, "dim": D, "rows_per_gpu": n,

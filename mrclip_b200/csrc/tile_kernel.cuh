@@ -445,11 +445,12 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           float a[64];
 #pragma unroll
           for (int c = 0; c < 64; ++c) a[c] = __uint_as_float(raw[c]);
-          if (diag_here && row_valid) {
+          if (diag_here && row_valid) {   // select chain, not an indexed read: keeps a[] in registers
             const int idx = label - col_base;
+            float dv = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c)
-              if (c == idx) p.diag2[grow] = a[c] * sl;
+            for (int c = 0; c < 64; ++c) dv = (c == idx) ? a[c] : dv;
+            if (idx >= 0 && idx < 64) p.diag2[grow] = dv * sl;
           }
           if (ragged) {
 #pragma unroll
@@ -512,9 +513,10 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int c = 0; c < 64; ++c) v[c] = __uint_as_float(raw[c]) * sl;
           if (diag_here && row_valid) {
             const int idx = label - col_base;
+            float dv = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c)
-              if (c == idx) p.diag2[grow] = v[c];
+            for (int c = 0; c < 64; ++c) dv = (c == idx) ? v[c] : dv;
+            if (idx >= 0 && idx < 64) p.diag2[grow] = dv;
           }
           if (ragged) {
 #pragma unroll
@@ -550,40 +552,81 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               make_float2(v[0], v[1]);
           if (lane == 0) p.col_c[(size_t)band * (p.n_pad / 64) + col_base / 64] = cw;
         } else if (kFwd && LOSS == LOSS_SIGLIP) {
+          // softplus(-y z) = max(z, 0) + log1p(e) - [positive] z  and  sigmoid(z) = (z >= 0 ? 1 : e) / (1 + e)  with
+          // e = 2^-|u|: one ex2 per logit.  When the whole 32 x 64 sub-tile has e <= 1/8 (|z| >= 2.08: the normal
+          // case, SigLIP's bias starts at -10) log1p and the reciprocal are short series on the FMA pipe; the exact
+          // lg2 / rcp forms (three MUFU per logit, as much XU time as the tile's MMAs) are kept for the rest.
           float part = 0.f;
-          float gv[64];
+          float gv[64];             // e, then overwritten by G
           float dsum = 0.f, bsum = 0.f;
+          float emax = 0.f;
 #pragma unroll
           for (int c = 0; c < 64; ++c) {
-            const float a = __uint_as_float(raw[c]);
-            const float z = fmaf(a, s, bias);
-            const float u = fmaf(a, sl, b2);
-            const float e = ex2f(-fabsf(u));
-            float sp = fmaxf(z, 0.f) + log1p_from_exp(e);
-            const bool dead = (ragged && (col_base + c >= p.n_cols)) || !row_valid;
-            if (dead) sp = 0.f;
-            part += sp;
-            if (Cfg::kEOut) {
-              float g = (u >= 0.f ? 1.f : e) * rcpf(1.f + e);   // sigmoid(z)
-              if (dead) g = 0.f;
-              gv[c] = g;
-              dsum = fmaf(g, a, dsum);
-              bsum += g;
+            const float u = fmaf(__uint_as_float(raw[c]), sl, b2);
+            gv[c] = ex2f(-fabsf(u));
+            emax = fmaxf(emax, gv[c]);
+          }
+          const bool small = __all_sync(0xffffffffu, emax <= 0.125f);
+          if (small) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              const float a = __uint_as_float(raw[c]);
+              const float z = fmaf(a, s, bias);
+              const float e = gv[c];
+              const float lp = e * (1.f + e * (-0.5f + e * (0.33333334f + e * (-0.25f + e * 0.2f))));
+              const float r = 1.f + e * (-1.f + e * (1.f + e * (-1.f + e)));     // 1/(1+e), error < e^5
+              float sp = fmaxf(z, 0.f) + lp;
+              float g = (z >= 0.f ? 1.f : e) * r;
+              const bool dead = (ragged && (col_base + c >= p.n_cols)) || !row_valid;
+              if (dead) {
+                sp = 0.f;
+                g = 0.f;
+              }
+              part += sp;
+              if (Cfg::kEOut) {
+                gv[c] = g;
+                dsum = fmaf(g, a, dsum);
+                bsum += g;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              const float a = __uint_as_float(raw[c]);
+              const float z = fmaf(a, s, bias);
+              const float e = gv[c];
+              float sp = fmaxf(z, 0.f) + log1p_from_exp(e);
+              float g = (z >= 0.f ? 1.f : e) * rcpf(1.f + e);   // sigmoid(z)
+              const bool dead = (ragged && (col_base + c >= p.n_cols)) || !row_valid;
+              if (dead) {
+                sp = 0.f;
+                g = 0.f;
+              }
+              part += sp;
+              if (Cfg::kEOut) {
+                gv[c] = g;
+                dsum = fmaf(g, a, dsum);
+                bsum += g;
+              }
             }
           }
-          if (diag_here) {
+          if (diag_here) {   // the positive of this row, if it falls into these 64 columns (select chains only)
             const int idx = label - col_base;
+            const bool has = row_valid && idx >= 0 && idx < 64;
+            float ad = 0.f;
 #pragma unroll
-            for (int c = 0; c < 64; ++c)
-              if (c == idx && row_valid) {
-                const float a = __uint_as_float(raw[c]);
-                part -= fmaf(a, s, bias);
-                if (Cfg::kEOut) {
-                  gv[c] -= 1.f;
-                  dsum -= a;
-                  bsum -= 1.f;
-                }
+            for (int c = 0; c < 64; ++c) {
+              const bool here = has && (c == idx);
+              ad = here ? __uint_as_float(raw[c]) : ad;
+              if (Cfg::kEOut) gv[c] = here ? gv[c] - 1.f : gv[c];
+            }
+            if (has) {
+              part -= fmaf(ad, s, bias);
+              if (Cfg::kEOut) {
+                dsum -= ad;
+                bsum -= 1.f;
               }
+            }
           }
           acc0 += part;
           if (Cfg::kEOut) {
