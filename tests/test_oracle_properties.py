@@ -115,3 +115,22 @@ def test_siglip_rank_mean_is_global(w):
     for r in range(w):
         assert np.allclose(many[r]["d_image"], w * one["d_image"][r * n:(r + 1) * n], rtol=1e-8, atol=1e-14)
     assert np.isclose(np.mean([o["d_logit_bias"] for o in many]), one["d_logit_bias"], rtol=1e-8)
+
+
+def test_dscale_identity_for_forward_side_sums():
+    """with A_r = sum_{i in r, all j} Prow_ij C_ij and A'_r = sum_{all i, j in r} Prow_ij C_ij
+    (C = I T^T), the local-loss d_scale of rank r is  <dT_r, T_r>/s + 1/(2n) (A_r - A'_r)  -- only row-softmax sums,
+    which the forward can accumulate in fp32 per column chunk."""
+    rng = np.random.default_rng(0)
+    w, n, d, s = 4, 6, 5, 9.0
+    img, txt = _feats(rng, w * n, d)
+    ref = clip_loss_oracle(_parts(img, w), _parts(txt, w), s, True, True)
+    c = img @ txt.T
+    z = s * c
+    p_row = np.exp(z - np.log(np.exp(z).sum(axis=1, keepdims=True)))
+    for r in range(w):
+        rows = slice(r * n, (r + 1) * n)
+        a_r = (p_row[rows] * c[rows]).sum()
+        ap_r = (p_row[:, rows] * c[:, rows]).sum()
+        ds = (ref[r]["d_text"] * txt[rows]).sum() / s + 0.5 / n * (a_r - ap_r)
+        assert np.isclose(ds, ref[r]["d_logit_scale"], rtol=1e-10)
