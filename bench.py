@@ -38,6 +38,9 @@ def parse():
     ap.add_argument("--feature-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", action="store_true",
+                    help="also capture the whole step (forward + backward, collectives and device barriers) as one "
+                         "CUDA graph and time its replays (reported under \"graph\"; the headline stays the eager step)")
     ap.add_argument("--workload", default="clip", choices=["clip", "siglip", "mpos"],
                     help="clip = the headline (BASELINE configs[2]); siglip / mpos: extra measurements of the other two "
                          "losses on the same shapes (not the headline metric)")
@@ -221,6 +224,33 @@ def run_ours(args):
     ms_per_step = total_ms / args.steps
     value = N / (ms_per_step * 1e-3)
 
+    graph_info = None
+    if args.graph:
+        # opt-in (not validated on hardware yet): the step replayed from one captured graph removes the host from the
+        # loop -- ~35 launches, three device barriers and the autograd / ctypes overhead per step (profiles/r1_notes.md §5)
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step(img_d, txt_d)
+            torch.cuda.current_stream().wait_stream(side)
+            barrier()
+            gr = torch.cuda.CUDAGraph()
+            l0 = eng.launch_count()
+            with torch.cuda.graph(gr, stream=side, capture_error_mode="thread_local"):
+                g_loss = step(img_d, txt_d)
+            captured = eng.launch_count() - l0
+            barrier()
+            for _ in range(3):
+                gr.replay()
+            g_ms = timed(gr.replay, args.steps) / args.steps
+            graph_info = {"ms_per_step": g_ms, "value": N / (g_ms * 1e-3), "unit": UNIT, "captured_launches": captured,
+                          "loss": float(g_loss.item())}
+        except Exception as exc:  # report, keep the eager numbers
+            graph_info = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+            torch.cuda.synchronize()
+
     # per-operation device time, live: CUDA events around every engine call (= kernel launch group) on the
     # launching stream; the roofline is quoted for the costliest op that carries algorithmic flops
     ALG_OPS = {"clip_fwd_tiles": "tile_kernel<MODE_FWD> (S = A.B^T tiles + online LSE, 2nND flop)",
@@ -355,6 +385,8 @@ def run_ours(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if graph_info is not None:
+            line["graph"] = graph_info
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
