@@ -1,10 +1,14 @@
 """mrclip_b200 -- B200-native (sm_100a) distributed contrastive loss for MR-CLIP.
 
 Public surface mirrors the reference's ``open_clip.loss`` for the hot path:
-``ClipLoss``, ``SigLipLoss``, ``MultiPositiveClipLoss``, ``gather_features``.  The kernels live in ``csrc/`` behind the C ABI
+``ClipLoss``, ``SigLipLoss``, ``MultiPositiveClipLoss``, ``gather_features`` and the ``neighbour_exchange*`` ring hops.  The kernels live in ``csrc/`` behind the C ABI
 declared in ``include/mrclip.h`` and are loaded with ctypes (``_cabi.py``).
 """
+from .exchange import (NeighbourExchange, NeighbourExchangeBidir, neighbour_exchange,  # noqa: F401
+                       neighbour_exchange_bidir, neighbour_exchange_bidir_with_grad, neighbour_exchange_with_grad)
 from .loss import ClipLoss, MultiPositiveClipLoss, SigLipLoss, gather_features, set_engine  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features"]
+__all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features", "neighbour_exchange",
+           "neighbour_exchange_bidir", "neighbour_exchange_with_grad", "neighbour_exchange_bidir_with_grad",
+           "NeighbourExchange", "NeighbourExchangeBidir"]

@@ -46,6 +46,8 @@ except ImportError:  # pragma: no cover
 
 from ._cabi import Shape
 from .engine import default_engine
+from .exchange import (NeighbourExchange, NeighbourExchangeBidir, neighbour_exchange,  # noqa: F401  (reference names)
+                       neighbour_exchange_bidir, neighbour_exchange_bidir_with_grad, neighbour_exchange_with_grad)
 
 __all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features", "set_engine"]
 

@@ -212,3 +212,48 @@ def test_gather_features_semantics_gloo():
                 assert np.allclose(grad, np.broadcast_to(w_rows, (3, 4)))
             else:         # local loss without grad: gathered copy is detached
                 assert grad is None
+
+
+def _exchange_worker(rank, world, init_file, ret):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        from mrclip_b200.loss import (neighbour_exchange, neighbour_exchange_bidir,
+                                      neighbour_exchange_bidir_with_grad, neighbour_exchange_with_grad)
+        left, right = (rank - 1) % world, (rank + 1) % world
+        mine = torch.full((2, 3), float(rank))
+        res = {"plain": neighbour_exchange(left, right, mine).numpy()}            # what the left neighbour sent
+        fr, fl = neighbour_exchange_bidir(left, right, mine + 100, mine + 200)
+        res["bidir"] = (fr.numpy(), fl.numpy())
+        # gradients travel the hop backwards: what I sent right is weighted on the right neighbour
+        x = torch.full((2, 3), 1.0, requires_grad=True)
+        y = neighbour_exchange_with_grad(left, right, x)
+        (y * float(rank + 1)).sum().backward()
+        res["grad"] = x.grad.numpy()
+        a = torch.ones(2, 3, requires_grad=True)
+        b = torch.ones(2, 3, requires_grad=True)
+        from_right, from_left = neighbour_exchange_bidir_with_grad(left, right, a, b)
+        (from_right * float(10 * (rank + 1)) + from_left * float(rank + 1)).sum().backward()
+        res["grad_bidir"] = (a.grad.numpy(), b.grad.numpy())
+        ret[rank] = res
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_neighbour_exchange_semantics_gloo():
+    """reference loss.py:226-311: ring hops, their return order, and the reverse hop as gradient"""
+    world = 3
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_exchange_worker, args=(world, os.path.join(td, "init"), ret), nprocs=world, join=True)
+    for r in range(world):
+        left, right = (r - 1) % world, (r + 1) % world
+        res = ret[r]
+        assert np.all(res["plain"] == left)
+        fr, fl = res["bidir"]
+        assert np.all(fr == right + 100) and np.all(fl == left + 200)     # right sent "to left", left sent "to right"
+        assert np.all(res["grad"] == right + 1)                           # my tensor was weighted on the right neighbour
+        ga, gb = res["grad_bidir"]
+        assert np.all(ga == 10 * (left + 1))    # a went left, where it arrived as that rank's from_right
+        assert np.all(gb == right + 1)          # b went right, where it arrived as that rank's from_left
