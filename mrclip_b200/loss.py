@@ -49,7 +49,8 @@ from .engine import default_engine
 from .exchange import (NeighbourExchange, NeighbourExchangeBidir, neighbour_exchange,  # noqa: F401  (reference names)
                        neighbour_exchange_bidir, neighbour_exchange_bidir_with_grad, neighbour_exchange_with_grad)
 
-__all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features", "set_engine"]
+__all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features", "gather_features_with_tokens",
+           "multi_positive_cross_entropy_loss", "set_engine"]
 
 _engine_override = None
 
@@ -109,6 +110,36 @@ def gather_features(image_features, text_features, local_loss=False, gather_with
             all_image_features = torch.cat(parts_i, dim=0)
             all_text_features = torch.cat(parts_t, dim=0)
     return all_image_features, all_text_features
+
+
+def gather_features_with_tokens(image_features, text_features, text_tokens=None, local_loss=False,
+                                gather_with_grad=False, rank=0, world_size=1, use_horovod=False):
+    """Reference ``gather_features_with_tokens`` (loss.py:450-509): ``gather_features`` plus the rank-ordered
+    concatenation of every rank's integer labels (None stays None).  Labels carry no gradient."""
+    all_image_features, all_text_features = gather_features(
+        image_features, text_features, local_loss=local_loss, gather_with_grad=gather_with_grad, rank=rank,
+        world_size=world_size, use_horovod=use_horovod)
+    return all_image_features, all_text_features, _all_gather_tokens(text_tokens, world_size)
+
+
+def _all_gather_tokens(text_tokens, world_size):
+    if text_tokens is None:
+        return None
+    tok = text_tokens.contiguous()
+    out = torch.empty((world_size * tok.shape[0],) + tuple(tok.shape[1:]), dtype=tok.dtype, device=tok.device)
+    dist.all_gather_into_tensor(out, tok)
+    return out
+
+
+def multi_positive_cross_entropy_loss(logits, pos_mask):
+    """Reference ``multi_positive_cross_entropy_loss`` (loss.py:626-644) on materialised logits:
+    mean_i( -(1/|P(i)|) sum_{j in P(i)} log softmax(logits_i)_j ), with the reference's quirks -- the row maximum is
+    detached, 1e-12 is added inside the log, and an empty positive set divides by 1.  Helper for callers that hold
+    logits; ``MultiPositiveClipLoss.forward`` computes the same value without forming them."""
+    shifted = logits - logits.amax(dim=1, keepdim=True).detach()
+    log_prob = shifted - torch.log(shifted.exp().sum(dim=1, keepdim=True) + 1e-12)
+    positives = pos_mask.sum(dim=1).clamp(min=1)
+    return (-(pos_mask * log_prob).sum(dim=1) / positives).mean()
 
 
 # --------------------------------------------------------------------------------------------
@@ -673,6 +704,14 @@ class MultiPositiveClipLoss(ClipLoss):
     TE / TR / TI class, train.py:123) is equal are positives of each other.  Same constructor and call signature;
     returns ``{"multi contrastive_loss": loss}`` with ``output_dict=True`` like the reference."""
 
+    def get_logits_custom(self, image_features, text_features, text_tokens, logit_scale):
+        """Materialised logits plus the gathered labels (loss.py:672-694); not used by ``forward``."""
+        if self.world_size > 1:
+            logits_per_image, logits_per_text = self.get_logits(image_features, text_features, logit_scale)
+            return logits_per_image, logits_per_text, _all_gather_tokens(text_tokens, self.world_size)
+        logits_per_image, logits_per_text = self.get_logits(image_features, text_features, logit_scale)
+        return logits_per_image, logits_per_text, text_tokens
+
     def forward(self, image_features, text_features, logit_scale, delta=0.5, tokenized_texts=None, output_dict=False):
         if tokenized_texts is None:
             raise ValueError("MultiPositiveClipLoss needs tokenized_texts (one integer label per sample)")
@@ -803,6 +842,14 @@ class SigLipLoss(nn.Module):
         if logit_bias is not None:
             logits = logits + logit_bias
         return logits
+
+    def _loss(self, image_features, text_features, logit_scale, logit_bias=None, negative_only=False):
+        """One materialised chunk of the pairwise sigmoid loss (loss.py:354-363): -sum logsigmoid(label * logit) / n.
+        Not used by ``forward`` (the tile kernel sums softplus over the row block without forming logits)."""
+        logits = self.get_logits(image_features, text_features, logit_scale, logit_bias)
+        labels = self.get_ground_truth(image_features.device, image_features.dtype, image_features.shape[0],
+                                       negative_only=negative_only)
+        return -torch.nn.functional.logsigmoid(labels * logits).sum() / image_features.shape[0]
 
     def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict=False):
         loss = _SigLipLossFn.apply(image_features, text_features, logit_scale, logit_bias, self)

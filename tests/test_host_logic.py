@@ -257,3 +257,91 @@ def test_neighbour_exchange_semantics_gloo():
         ga, gb = res["grad_bidir"]
         assert np.all(ga == 10 * (left + 1))    # a went left, where it arrived as that rank's from_right
         assert np.all(gb == right + 1)          # b went right, where it arrived as that rank's from_left
+
+
+# ------------------------------------------------------------------------------------------------
+# materialised helpers kept for callers of the reference's module (not on the fused path)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mpos_w1", "mpos_w1_delta03_ragged"])
+def test_materialised_multipositive_helpers_match_reference_golden(name):
+    """get_logits + multi_positive_cross_entropy_loss (loss.py:626-644, 696-747) reproduce the recorded outputs"""
+    from mrclip_b200.loss import multi_positive_cross_entropy_loss
+    case = load_golden(name)
+    meta, ref = case["meta"], case["ranks"][0]
+    img = torch.from_numpy(case["image"]).requires_grad_(True)
+    txt = torch.from_numpy(case["text"]).requires_grad_(True)
+    scale = torch.tensor(float(meta["scale"]), requires_grad=True)
+    labels = torch.from_numpy(ref["labels_in"])
+    mod = MultiPositiveClipLoss()
+    li, lt, tok = mod.get_logits_custom(img, txt, labels, scale)
+    assert tok is labels
+    mask = torch.eq(labels[:, None], labels[None, :]).float()
+    d = float(meta["delta"])
+    loss = d * multi_positive_cross_entropy_loss(li, mask) + (1 - d) * multi_positive_cross_entropy_loss(lt, mask)
+    (loss * float(meta["grad_output"])).backward()
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    assert rel_err(img.grad.numpy(), ref["d_image"]) <= 1e-5 and rel_err(txt.grad.numpy(), ref["d_text"]) <= 1e-5
+    assert abs(scale.grad.item() - float(ref["d_scale"])) <= 1e-4 * abs(float(ref["d_scale"])) + 1e-7
+
+
+def test_multi_positive_cross_entropy_quirks():
+    from mrclip_b200.loss import multi_positive_cross_entropy_loss
+    logits = torch.tensor([[2.0, 0.0, -1.0], [0.5, 0.5, 0.5]])
+    mask = torch.tensor([[1.0, 0.0, 1.0], [0.0, 0.0, 0.0]])          # second row: no positives -> contributes 0 / 1
+    lp = torch.log_softmax(logits.double(), dim=1)
+    want = (-(lp[0, 0] + lp[0, 2]) / 2 + 0.0) / 2
+    assert abs(multi_positive_cross_entropy_loss(logits, mask).item() - want.item()) < 1e-6
+
+
+def test_siglip_materialised_chunk_loss_matches_reference_golden():
+    """SigLipLoss._loss on one rank is the whole loss (loss.py:354-363, :365-368)"""
+    case = load_golden("siglip_w1")
+    meta, ref = case["meta"], case["ranks"][0]
+    img, txt = torch.from_numpy(case["image"]), torch.from_numpy(case["text"])
+    mod = SigLipLoss()
+    loss = mod._loss(img, txt, torch.tensor(float(meta["scale"])), torch.tensor(float(meta["bias"])))
+    assert abs(loss.item() - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+    neg = mod._loss(img, txt, torch.tensor(float(meta["scale"])), torch.tensor(float(meta["bias"])), negative_only=True)
+    z = float(meta["scale"]) * img.double() @ txt.double().t() + float(meta["bias"])
+    assert abs(neg.item() - (torch.nn.functional.softplus(z).sum() / img.shape[0]).item()) <= 1e-5 * abs(neg.item())
+
+
+def _tokens_worker(rank, world, init_file, ret):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        from mrclip_b200.loss import gather_features_with_tokens, multi_positive_cross_entropy_loss
+        case = load_golden("mpos_w2_ll1_gg1")
+        meta, ref = case["meta"], case["ranks"][rank]
+        n = case["image"].shape[0] // world
+        img = torch.from_numpy(case["image"][rank * n:(rank + 1) * n]).requires_grad_(True)
+        txt = torch.from_numpy(case["text"][rank * n:(rank + 1) * n]).requires_grad_(True)
+        labels = torch.from_numpy(ref["labels_in"])
+        gi, gt, tok = gather_features_with_tokens(img, txt, labels, local_loss=True, gather_with_grad=True, rank=rank,
+                                                  world_size=world)
+        mod = MultiPositiveClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+        li, lt, tok2 = mod.get_logits_custom(img, txt, labels, torch.tensor(float(meta["scale"])))
+        mask = torch.eq(labels[:, None], tok2[None, :]).float()
+        d = float(meta["delta"])
+        loss = d * multi_positive_cross_entropy_loss(li, mask) + (1 - d) * multi_positive_cross_entropy_loss(lt, mask)
+        loss.backward()
+        ret[rank] = dict(loss=loss.item(), tok=tok.numpy(), tok2=tok2.numpy(), gi=gi.detach().numpy(),
+                         d_image=img.grad.numpy(), d_text=txt.grad.numpy())
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_with_tokens_and_materialised_multipositive_gloo():
+    world = 2
+    case = load_golden("mpos_w2_ll1_gg1")
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_tokens_worker, args=(world, os.path.join(td, "init"), ret), nprocs=world, join=True)
+    all_labels = np.concatenate([case["ranks"][r]["labels_in"] for r in range(world)])
+    for r in range(world):
+        out, ref = ret[r], case["ranks"][r]
+        assert np.array_equal(out["tok"], all_labels) and np.array_equal(out["tok2"], all_labels)   # rank order, bit-exact
+        assert np.array_equal(out["gi"], case["image"])
+        assert abs(out["loss"] - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
+        assert rel_err(out["d_image"], ref["d_image"]) <= 1e-5 and rel_err(out["d_text"], ref["d_text"]) <= 1e-5
