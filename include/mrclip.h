@@ -178,6 +178,22 @@ int mrclip_push_copy(const void* src, size_t bytes, const unsigned long long* pe
 int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
                      void* stream);
 
+/* d logit_scale of a multi-rank local loss (loss.py:117-139 behind mul-backward) without entropy
+ * arithmetic in the rescale pass -- selected by MRCLIP_DS=fwd, NOT validated on hardware yet (default off):
+ *   s dL_r/ds = <dT_r, T_r> + ln2/(2n) * (R2(r,*) - R2(*,r)),   R2(q, r) = sum_{i in q, j in r} Prow_ij S2_ij.
+ * mrclip_clip_fwd_tiles_eu is mrclip_clip_fwd_tiles_e that also keeps u = sum_j 2^(S2_ij - m) S2_ij per row and column
+ * chunk half in ws; after mrclip_clip_fwd_reduce, mrclip_row_ent_split turns them into R2(me, q) for every owner q
+ * (out_slots: float [64][2][ranks], plane 0, summed over the 64 slots by the caller); mrclip_sum_slots_dot is
+ * mrclip_sum_slots that also accumulates <dT_r, T_r> (feat: packed bf16 rows of this rank) into dot_slots[64].
+ * mrclip_fwd_row_ent_ok: 1 when every column chunk of the forward plan has a single owner. */
+int mrclip_fwd_row_ent_ok(int m_rows, int n_cols, int n_per_rank);
+int mrclip_clip_fwd_tiles_eu(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                             int col_begin, int col_end, void* ws, void* emat, void* stream);
+int mrclip_row_ent_split(mrclip_shape shape, void* ws, const float* lse2_row, int n_per_rank, int ranks,
+                         float* out_slots, void* stream);
+int mrclip_sum_slots_dot(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                         const void* feat, long feat_ld, float* dot_slots, void* stream);
+
 /* SigLipLoss has no normaliser: its forward can store G = sigmoid(z) - [j==label_i] directly (then both
  * gradients are plain mrclip_gmat_gemm calls) and leaves the d_scale / d_bias partial sums in ws. */
 int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,

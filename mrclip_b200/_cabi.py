@@ -53,6 +53,10 @@ SIGNATURES = {
     "mrclip_gmat_gemm_push": (_I, [_P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _I, _P]),
     "mrclip_push_copy": (_I, [_P, C.c_size_t, _P, _I, C.c_size_t, _I, _P]),
     "mrclip_sum_slots": (_I, [_P, _I, _I, _I, _P, _I, _L, _P]),
+    "mrclip_fwd_row_ent_ok": (_I, [_I, _I, _I]),
+    "mrclip_clip_fwd_tiles_eu": (_I, [_P, _P, Shape, _I, _P, _I, _I, _P, _P, _P]),
+    "mrclip_row_ent_split": (_I, [Shape, _P, _P, _I, _I, _P, _P]),
+    "mrclip_sum_slots_dot": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
     "mrclip_launch_count": (_L, []),
 }
 

@@ -547,6 +547,61 @@ __global__ void sum_slots_kernel(const float* __restrict__ slots, int nslots, in
   }
 }
 
+// sum_slots_kernel that also accumulates <out, feat> (fp32, before the output cast) into dot_out[blockIdx.x % 64]:
+// the text-gradient side of  s dL_r/ds = <dT_r, T_r> + ...  (tile_kernel.cuh, MODE_FWDEU).  feat: packed bf16 [rows, ld].
+__global__ void sum_slots_dot_kernel(const float* __restrict__ slots, int nslots, int rows, int d,
+                                     void* __restrict__ out, int out_dtype, long out_ld,
+                                     const __nv_bfloat16* __restrict__ feat, long feat_ld, float* __restrict__ dot_out) {
+  const long total = (long)rows * d;
+  const long slot_stride = total;
+  float dot = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nslots; ++k) a += slots[k * slot_stride + i];
+    const long r = i / d;
+    const int c = (int)(i - r * d);
+    store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
+    dot = fmaf(a, __bfloat162float(feat[r * feat_ld + c]), dot);
+  }
+  dot = warp_sum(dot);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dot_out + (blockIdx.x & 63), v);
+  }
+}
+
+// R2(me, q) = sum over my rows i and the columns j owned by rank q of Prow_ij * S2_ij, from the forward's per-slot
+// (max2, sum) and u partials (tile_kernel.cuh, MODE_FWDEU): out[(blockIdx.x % 64) * 2 * ranks + q] += block sum.
+// A slot is one half of a column chunk; slots_per_rank consecutive slots belong to one owner.
+__global__ void row_ent_split_kernel(const float2* __restrict__ row_part, const float* __restrict__ row_ent, int slots,
+                                     int slots_per_rank, int ranks, int m_rows, int m_pad,
+                                     const float* __restrict__ lse2_row, float* __restrict__ out) {
+  extern __shared__ float acc[];   // [ranks]
+  for (int q = threadIdx.x; q < ranks; q += blockDim.x) acc[q] = 0.f;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float lse = i < m_rows ? lse2_row[i] : 0.f;
+  for (int q = 0; q < ranks; ++q) {
+    float r = 0.f;
+    if (i < m_rows) {
+      for (int s = q * slots_per_rank; s < (q + 1) * slots_per_rank && s < slots; ++s) {
+        const float m = row_part[(size_t)s * m_pad + i].x;
+        const float u = row_ent[(size_t)s * m_pad + i];
+        r = fmaf(exp2f(m - lse), u, r);       // m = -inf for an empty slot: weight 0, u = 0
+      }
+    }
+    r = warp_sum(r);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc + q, r);
+  }
+  __syncthreads();
+  for (int q = threadIdx.x; q < ranks; q += blockDim.x)
+    atomicAdd(out + (size_t)(blockIdx.x & 63) * 2 * ranks + q, acc[q]);
+}
+
 // all-gather by peer stores: copy `bytes` (multiple of 16) from src to dst[k] + offset for every k != skip.
 // dsts are NVLink-mapped addresses of the same buffer on every rank; a warp writes 512 contiguous bytes, so the
 // link sees full 128-byte packets.  grid.y = destination.

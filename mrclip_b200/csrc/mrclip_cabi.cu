@@ -199,7 +199,7 @@ GemmPlan gemm_plan(int out_rows, int k_len, int ld, bool force_single_split = fa
 }
 
 struct WsLayout {
-  size_t row_part, col_l, col_c, diag2, sc_part, sc_part2, cbmin, flag, dpart, total;
+  size_t row_part, col_l, col_c, diag2, sc_part, sc_part2, cbmin, flag, dpart, row_ent, total;
 };
 WsLayout ws_layout(int m_rows, int n_cols, int d) {
   const int ld = mrclip_padded_dim(d);
@@ -241,6 +241,9 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   off += align_up((size_t)(f.n_pad / 64) * sizeof(float), 256);
   w.flag = off;
   off += 256;
+  // MODE_FWDEU: u of every (row, slot); appended so that every other offset stays where it was
+  w.row_ent = off;
+  off += align_up((size_t)f.total_chunks * 2 * f.m_pad * sizeof(float), 256);
   w.total = off;
   return w;
 }
@@ -276,7 +279,7 @@ int check_shape(const mrclip_shape& s, int ld) {
 
 int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
             const float* scale, const float* bias, int col_begin, int col_end, void* ws, void* emat,
-            cudaStream_t st) {
+            cudaStream_t st, bool row_ent = false) {
   if (int e = check_shape(sh, ld)) return e;
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
@@ -316,6 +319,8 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   p.diag2 = reinterpret_cast<float*>(wsb + w.diag2);
   p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
   p.sc_part2 = reinterpret_cast<float2*>(wsb + w.sc_part2) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
+  p.row_ent = reinterpret_cast<float*>(wsb + w.row_ent);
+  if (emat && row_ent && loss_kind == LOSS_CLIP) return launch_tile<MODE_FWDEU, LOSS_CLIP, 256, kSBN>(ma, mb, me, p, st);
   if (emat) {
     if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWDE, LOSS_CLIP, 256, kSBN>(ma, mb, me, p, st);
     return launch_tile<MODE_FWDE, LOSS_SIGLIP, 256, kSBN>(ma, mb, me, p, st);
@@ -736,6 +741,59 @@ int mrclip_clip_fwd_tiles_e(const void* a_rows, const void* b_all, mrclip_shape 
   if (!emat) return fail(-1, "emat is NULL");
   return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws, emat,
                  (cudaStream_t)stream);
+}
+
+/* ---- d logit_scale of a multi-rank local loss without entropy arithmetic in the rescale pass (MRCLIP_DS=fwd; not
+ *      validated on hardware yet): the forward also keeps u = sum_j 2^(S2 - m) S2 per (row, column-chunk half) ---- */
+int mrclip_fwd_row_ent_ok(int m_rows, int n_cols, int n_per_rank) {
+  if (m_rows <= 0 || n_cols <= 0 || n_per_rank <= 0 || n_cols % n_per_rank != 0) return 0;
+  const FwdPlan f = fwd_plan(m_rows, n_cols);
+  return n_per_rank % (f.tiles_per_chunk * kSBN) == 0 ? 1 : 0;   // every column chunk has one owner
+}
+
+int mrclip_clip_fwd_tiles_eu(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
+                             int col_begin, int col_end, void* ws, void* emat, void* stream) {
+  if (!emat) return fail(-1, "emat is NULL");
+  return run_fwd(LOSS_CLIP, a_rows, b_all, shape, ld, scale, nullptr, col_begin, col_end, ws, emat,
+                 (cudaStream_t)stream, true);
+}
+
+int mrclip_row_ent_split(mrclip_shape sh, void* ws, const float* lse2_row, int n_per_rank, int ranks, float* out_slots,
+                         void* stream) {
+  if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
+  if (!lse2_row || !out_slots || ranks <= 0 || ranks > 1024 || n_per_rank * ranks != sh.n_cols ||
+      !mrclip_fwd_row_ent_ok(sh.m_rows, sh.n_cols, n_per_rank))
+    return fail(-1, "row_ent_split: column chunks do not split by owner (n_per_rank=%d, ranks=%d, n_cols=%d)",
+                n_per_rank, ranks, sh.n_cols);
+  cudaStream_t st = (cudaStream_t)stream;
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(ws);
+  CUDA_TRY(cudaMemsetAsync(out_slots, 0, (size_t)64 * 2 * ranks * sizeof(float), st));
+  const int slots_per_rank = 2 * (n_per_rank / (f.tiles_per_chunk * kSBN));
+  row_ent_split_kernel<<<ceil_div(sh.m_rows, 256), 256, ranks * sizeof(float), st>>>(
+      reinterpret_cast<const float2*>(wsb + w.row_part), reinterpret_cast<const float*>(wsb + w.row_ent),
+      f.total_chunks * 2, slots_per_rank, ranks, sh.m_rows, f.m_pad, lse2_row, out_slots);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_sum_slots_dot(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                         const void* feat, long feat_ld, float* dot_slots, void* stream) {
+  if (!slots || !out || !feat || !dot_slots || nslots <= 0 || rows <= 0 || d <= 0 || feat_ld < d)
+    return fail(-1, "sum_slots_dot: bad arguments");
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(dot_slots, 0, 64 * sizeof(float), st));
+  const long total = (long)rows * d;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  sum_slots_dot_kernel<<<(int)blocks, 256, 0, st>>>(slots, nslots, rows, d, out, out_dtype, out_ld,
+                                                    reinterpret_cast<const __nv_bfloat16*>(feat), feat_ld, dot_slots);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 int mrclip_emat_check(mrclip_shape sh, void* ws, const float* lse2_row, const float* lse2_col, void* stream) {

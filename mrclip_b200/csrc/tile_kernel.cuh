@@ -43,7 +43,11 @@ constexpr float kLn2 = 0.6931471805599453f;
 //       column sums) so that the backward never recomputes S: G = E * (2^(c-lse_row) + 2^(c-lse_col)) is formed
 //       on the fly inside the gradient GEMMs (gemm_kernel<.., XF>).  SigLIP has no normaliser, so its FWDE writes
 //       G = sigmoid(z) - delta directly.
-enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2, MODE_FWDE = 3 };
+// FWDEU: FWDE that also accumulates, per row and column chunk, u = sum_j 2^(S2_ij - m) * S2_ij (the row-softmax
+//        weighted logit sum, merged online like the LSE).  With it d logit_scale of a multi-rank local loss needs no
+//        entropy arithmetic in the rescale pass:  s dL_r/ds = <dT_r, T_r> + ln2/(2n) * (R2(r,*) - R2(*,r)),
+//        R2(q, r) = sum over rows of q and columns of r of Prow * S2  (not validated on hardware yet; MRCLIP_DS=fwd).
+enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2, MODE_FWDE = 3, MODE_FWDEU = 4 };
 enum : int { LOSS_CLIP = 0, LOSS_SIGLIP = 1 };
 
 struct TileParams {
@@ -80,6 +84,7 @@ struct TileParams {
   long g_ld;
   const int* run_if;    // optional device flag: the kernel returns at once when *run_if == 0
   int ent;              // GW clip: scalar partials become (sum P_own log2 P_own, sum P_oth log2 P_oth)
+  float* row_ent;       // FWDEU: [slots][m_pad]  u of each (row, column-chunk half), relative to row_part's max2
 };
 
 template <int LEN, int OFF>
@@ -122,7 +127,8 @@ struct TileCfg {
   static constexpr bool kLseSmem = (MODE == MODE_GW && LOSS == LOSS_CLIP);
   static constexpr int kLseBytes = kLseSmem ? kEpiWarps * (BN / 2) * 4 : 0;
   // FWDE: one 32x64 bf16 staging tile per epilogue warp (128-byte swizzled rows) for the TMA store of E
-  static constexpr bool kEOut = (MODE == MODE_FWDE);
+  static constexpr bool kEOut = (MODE == MODE_FWDE || MODE == MODE_FWDEU);
+  static constexpr bool kRowEnt = (MODE == MODE_FWDEU);
   static constexpr int kEBytes = kEOut ? kEpiWarps * 4096 : 0;
   static constexpr int kSmemBytes = kStages * kStageBytes + kGBytes + kLseBytes + kEBytes + kNumBars * 8 + 16 + 1024;
 };
@@ -149,7 +155,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const uint32_t lse_smem = g_base + Cfg::kGBytes;
   const uint32_t e_smem = lse_smem + Cfg::kLseBytes;   // 1024-byte aligned (stages and G are multiples of 1024)
   uint8_t* bar_ptr = smem + STAGES * kStageBytes + Cfg::kGBytes + Cfg::kLseBytes + Cfg::kEBytes;
-  constexpr bool kFwd = (MODE == MODE_FWD || MODE == MODE_FWDE);
+  constexpr bool kFwd = (MODE == MODE_FWD || MODE == MODE_FWDE || MODE == MODE_FWDEU);
   const uint32_t bar_base = smem_u32(bar_ptr);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bar_ptr + Cfg::kNumBars * 8);
 
@@ -168,7 +174,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    if (MODE == MODE_BWD || MODE == MODE_FWDE) tma_prefetch_desc(&tmBt);
+    if (MODE == MODE_BWD || Cfg::kEOut) tma_prefetch_desc(&tmBt);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -370,6 +376,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int label_w0 = rb * kBM + q * 32 + p.label_offset;  // label of lane 0 (warp uniform)
 
       float m_run = -CUDART_INF_F, l_run = 0.f;  // FWD clip: running row (max2, sum)
+      float u_run = 0.f;                         // FWDEU: running sum of 2^(S2 - m_run) * S2
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // scalar partials (loss | ds, db)
       float lr2 = CUDART_INF_F;
       if (!kFwd && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
@@ -434,7 +441,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             bulk_commit();
           }
         };
-        if (MODE == MODE_FWDE && LOSS == LOSS_CLIP) {
+        if (Cfg::kEOut && LOSS == LOSS_CLIP) {
           // ---- forward that keeps E: the lean epilogue (sl > 0: logit_scale is exp(.) in the reference, model.py:324)
           //   * the sub-tile reference is taken on the raw accumulators (max commutes with the positive scale), so
           //     the scaling folds into the exponent's FMA, issued as packed fp32 pairs (FFMA2 / FADD2);
@@ -452,22 +459,25 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             for (int c = 0; c < 64; ++c) dv = (c == idx) ? a[c] : dv;
             if (idx >= 0 && idx < 64) p.diag2[grow] = dv * sl;
           }
+          // masked entries: -inf, or a finite sentinel when the exponent is also multiplied (0 * -inf is NaN)
+          const float kMasked = Cfg::kRowEnt ? -1e30f : -CUDART_INF_F;
           if (ragged) {
 #pragma unroll
             for (int c = 0; c < 64; ++c)
-              if (col_base + c >= p.n_cols) a[c] = -CUDART_INF_F;
+              if (col_base + c >= p.n_cols) a[c] = kMasked;
           }
           if (!row_valid) {
 #pragma unroll
-            for (int c = 0; c < 64; ++c) a[c] = -CUDART_INF_F;
+            for (int c = 0; c < 64; ++c) a[c] = kMasked;
           }
           float tmax = a[0];
 #pragma unroll
           for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, a[c]);
           const float wmax = warp_max(tmax);
-          const float cw = (wmax == -CUDART_INF_F) ? 0.f : wmax * sl;
+          const float cw = (Cfg::kRowEnt ? (wmax <= -1e29f) : (wmax == -CUDART_INF_F)) ? 0.f : wmax * sl;
           const float2 sl2 = make_float2(sl, sl), ncw2 = make_float2(-cw, -cw);
           float2 rs2 = make_float2(0.f, 0.f);
+          float2 us2 = make_float2(0.f, 0.f);
           float v[64];
 #pragma unroll
           for (int c = 0; c < 32; ++c) {
@@ -475,10 +485,17 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             v[2 * c] = ex2f(t.x);
             v[2 * c + 1] = ex2f(t.y);
             rs2 = fadd2(rs2, make_float2(v[2 * c], v[2 * c + 1]));
+            if (Cfg::kRowEnt) us2 = ffma2(make_float2(v[2 * c], v[2 * c + 1]), t, us2);   // sum e * (S2 - cw)
           }
           const float rowsum = rs2.x + rs2.y;
           const float mnew = fmaxf(m_run, cw);
-          l_run = l_run * ex2f(m_run - mnew) + rowsum * ex2f(cw - mnew);
+          if (Cfg::kRowEnt) {
+            const float f_old = ex2f(m_run - mnew), f_new = ex2f(cw - mnew);
+            l_run = l_run * f_old + rowsum * f_new;
+            u_run = u_run * f_old + fmaf(cw, rowsum, us2.x + us2.y) * f_new;
+          } else {
+            l_run = l_run * ex2f(m_run - mnew) + rowsum * ex2f(cw - mnew);
+          }
           m_run = mnew;
           // column sums: lane = row writes 32 fp32 columns (8 swizzled 16-byte chunks), then lane = column reads them
           const uint32_t stg = e_smem + (warp - 2) * 4096;
@@ -744,6 +761,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (kFwd && LOSS == LOSS_CLIP) {
         const int slot = (p.chunk_base + chunk) * 2 + h;
         p.row_part[(size_t)slot * p.m_pad + grow] = make_float2(m_run, l_run);
+        if (Cfg::kRowEnt) p.row_ent[(size_t)slot * p.m_pad + grow] = u_run;
       } else if (kFwd) {
         const float tot = warp_sum(acc0);
         if (lane == 0) p.sc_part[(size_t)item * kEpiWarps + (warp - 2)] = make_float2(tot, 0.f);

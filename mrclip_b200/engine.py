@@ -176,6 +176,32 @@ class CudaEngine:
         _cabi.check(self.lib.mrclip_sum_slots(slots.data_ptr(), slots.shape[0], slots.shape[1], slots.shape[2],
                                               d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0), self._stream()))
 
+    # ---- MRCLIP_DS=fwd (opt-in, not validated on hardware yet): d logit_scale from forward-side row sums ----------
+    def fwd_row_ent_ok(self, m_rows, n_cols, n_per_rank):
+        """True when every column chunk of the forward plan has one owner (the per-owner split is then exact)."""
+        return bool(self.lib.mrclip_fwd_row_ent_ok(m_rows, n_cols, n_per_rank))
+
+    def clip_fwd_tiles_eu(self, a_rows, b_all, shape, scale, col_begin, col_end, ws, emat):
+        """clip_fwd_tiles_e that also keeps u = sum_j 2^(S2 - m) S2 per row and column-chunk half in ws."""
+        _cabi.check(self.lib.mrclip_clip_fwd_tiles_eu(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
+                                                      scale.data_ptr(), col_begin, col_end, ws.data_ptr(),
+                                                      emat.data_ptr(), self._stream()))
+
+    def row_ent_split(self, shape, ws, lse2_row, n_per_rank, ranks, out_slots):
+        """out_slots[:, 0, q] (float32 [64, 2, ranks], summed over dim 0 by the caller) = R2(me, q): sum over my rows
+        and the columns of rank q of Prow * S2 (log2 units).  After clip_fwd_reduce of a clip_fwd_tiles_eu forward."""
+        assert out_slots.dtype == torch.float32 and out_slots.is_contiguous() and out_slots.shape == (64, 2, ranks)
+        _cabi.check(self.lib.mrclip_row_ent_split(shape, ws.data_ptr(), lse2_row.data_ptr(), n_per_rank, ranks,
+                                                  out_slots.data_ptr(), self._stream()))
+
+    def sum_slots_dot(self, slots, d_out, feat, dot_slots):
+        """sum_slots that also leaves <d_out, feat> (fp32, feat = packed bf16 rows) spread over dot_slots[64]."""
+        assert slots.dtype == torch.float32 and slots.is_contiguous() and slots.dim() == 3
+        assert feat.dtype == torch.bfloat16 and feat.stride(1) == 1 and dot_slots.numel() == 64
+        _cabi.check(self.lib.mrclip_sum_slots_dot(slots.data_ptr(), slots.shape[0], slots.shape[1], slots.shape[2],
+                                                  d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0), feat.data_ptr(),
+                                                  feat.stride(0), dot_slots.data_ptr(), self._stream()))
+
     def siglip_fwd_e(self, a_rows, b_all, shape, scale, bias, ws, loss, gmat):
         _cabi.check(self.lib.mrclip_siglip_fwd_e(a_rows.data_ptr(), b_all.data_ptr(), shape, b_all.shape[1],
                                                  scale.data_ptr(), _ptr(bias), ws.data_ptr(), loss.data_ptr(),

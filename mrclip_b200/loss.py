@@ -53,6 +53,7 @@ __all__ = ["ClipLoss", "SigLipLoss", "MultiPositiveClipLoss", "gather_features",
            "multi_positive_cross_entropy_loss", "set_engine"]
 
 _engine_override = None
+_FWD_DS_MIN_PAIRS = 1 << 22     # MRCLIP_DS=fwd: below this the bf16 noise of G in <dT_r, T_r> is not averaged out
 
 
 def set_engine(engine):
@@ -176,6 +177,7 @@ class _Workspace:
         self.dt_partial = None
         self.push = None
         self.msums = torch.zeros((64, 2, world), dtype=f32, device=device)   # 64 slots against atomic contention
+        self.dot_slots = torch.zeros((64,), dtype=f32, device=device)        # <dT_r, T_r> partials (MRCLIP_DS=fwd)
         self.has_emat = False
 
     def gmat_buffer(self, eng):
@@ -334,14 +336,15 @@ def _ensure_transposed(eng, ws):
         ws.transposed = True
 
 
-def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
+def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt, dot_slots=None):
     """dT_r = sum over ranks q of (G_q^T . I_q)[rows of r].  Launches this rank's partial GEMM and returns the
     closure that completes d_txt; the caller runs the image-gradient GEMM in between.
 
     Default on GPUs: the GEMM's epilogue pushes each output tile into its owner's receive slot over NVLink peer
     memory (csrc/gemm2_kernel.cuh, mrclip_gmat_gemm_push: 128-byte bulk copies from a staging tile), then one
     device-side barrier and a slot sum on the owner.  MRCLIP_RS=nccl, CPU tests under gloo, or no symmetric memory:
-    fp32 partial + reduce_scatter, asynchronous, overlapped with the image-gradient GEMM."""
+    fp32 partial + reduce_scatter, asynchronous, overlapped with the image-gradient GEMM.
+    dot_slots (float32 [64], optional): also receives <dT_r, T_r> with T_r the packed text rows (its sum)."""
     n, d, world = ws.n, ws.d, ws.world
     rows = slice(rank * n, (rank + 1) * n)
     push = ws.push_buffers(rank)
@@ -351,7 +354,10 @@ def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
 
         def finish():
             hdl.barrier()                  # every rank's tiles have landed in my slots (and mine in theirs)
-            eng.sum_slots(recv, d_txt)
+            if dot_slots is None:
+                eng.sum_slots(recv, d_txt)
+            else:
+                eng.sum_slots_dot(recv, d_txt, ws.txt_all[rows], dot_slots)
         return finish
     part = ws.dt_partial_buffer()
     eng.gmat_gemm(True, gmat, shape, ws.img_all[rows], coef, scale, gout, ws.scratch, part)
@@ -361,22 +367,31 @@ def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt):
     def finish():
         work.wait()
         d_txt.copy_(dt32)
+        if dot_slots is not None:
+            dot_slots.zero_()
+            dot_slots[0] = (dt32 * ws.txt_all[rows][:, :d].float()).sum()
     return finish
 
 
-def _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, keep_e, gather_images):
+def _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, keep_e, gather_images,
+                 row_ent=False):
     """Pack + gather, the row-block tiles (keeping the bf16 exponentials when keep_e) and the statistics exchange:
     leaves lse2_row_all / lse2_col_all (every row / column of the global batch, log2 units) and diag2 in ws."""
     n, N = ws.n, ws.N
     rows = slice(rank * n, (rank + 1) * n)
     _gather_packed(eng, ws, image_features, text_features, rank, world, gather_images=gather_images)
-    if keep_e:
+    if keep_e and row_ent:
+        eng.clip_fwd_tiles_eu(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
+        ws.has_emat = True
+    elif keep_e:
         eng.clip_fwd_tiles_e(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch, ws.gmat_buffer(eng))
         ws.has_emat = True
     else:
         eng.clip_fwd_tiles(ws.img_all[rows], ws.txt_all, shape, scale, 0, N, ws.scratch)
     col_m, col_l, row_lse = ws.stats_local[0], ws.stats_local[1], ws.stats_local[2]
     eng.clip_fwd_reduce(shape, ws.scratch, row_lse, col_m, col_l, ws.diag2)
+    if keep_e and row_ent:   # R2(me, q) for every column owner q, from the forward's per-chunk row sums
+        eng.row_ent_split(shape, ws.scratch, row_lse, n, world, ws.msums)
     if world > 1 and ws.sym is not None and N % 4 == 0:     # (16-byte granular peer stores)
         _, shdl, sptrs = ws.sym["stats"]
         ws.stats_all[rank].copy_(ws.stats_local)
@@ -410,8 +425,14 @@ class _ClipLossFn(torch.autograd.Function):
         split_g = world > 1 and module.local_loss and not module.gather_with_grad
         split_g = split_g or (world > 1 and (n < 8 or world > 64))   # limits of the per-owner entropy sums
         use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g
+        # MRCLIP_DS=fwd (opt-in, not validated on hardware yet): d logit_scale of the multi-rank local loss from
+        # forward-side row sums and <dT_r, T_r>, so that the rescale pass carries no entropy arithmetic
+        ctx.fwd_ds = bool(use_emat and world > 1 and module.local_loss and module.gather_with_grad
+                          and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
+                          and os.environ.get("MRCLIP_DS", "entropy").lower() == "fwd"
+                          and n * N >= _FWD_DS_MIN_PAIRS and eng.fwd_row_ent_ok(n, N, n))
         _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, use_emat,
-                     gather_images=not use_emat and any(ctx.needs_input_grad))
+                     gather_images=not use_emat and any(ctx.needs_input_grad), row_ent=ctx.fwd_ds)
         loss = torch.empty((1,), dtype=torch.float32, device=device)
         eng.clip_loss(ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2, n, rank * n, loss)
         ctx.loss_local = loss.clone() if (world > 1 and not module.local_loss) else loss
@@ -455,7 +476,9 @@ class _ClipLossFn(torch.autograd.Function):
             # rounding of G averages out); otherwise the rescale pass accumulates the softmax entropies, which is
             # exact per rank and insensitive to that rounding
             use_dot = world == 1 and n * N >= (1 << 22)
-            msums = ws.msums if (need_s and not use_dot) else None
+            fwd_ds = ctx.fwd_ds and need_s and need_t
+            rsplit = ws.msums.sum(0)[0] if fwd_ds else None     # before the rescale pass can reuse the buffer
+            msums = ws.msums if (need_s and not use_dot and not fwd_ds) else None
             eng.emat_to_gmat(ws.img_all[rows], ws.txt_all, shape, ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2,
                              ctx.scale, 1.0, 1.0, ws.scratch, gmat, msums, n, world)
             if world == 1:
@@ -465,6 +488,19 @@ class _ClipLossFn(torch.autograd.Function):
                 if need_s and not use_dot:
                     ds = (gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * 0.5 / n) * ws.msums.sum())
                     ds_done = True
+            elif fwd_ds:
+                # s dL_r/ds = <dT_r, T_r> + ln2/(2n) (R2(r,*) - R2(*,r)),  R2(q, r) = sum_{i in q, j in r} Prow_ij S2_ij:
+                # R2(r, .) is local (forward), R2(*, r) one W-float all-reduce, the dot rides on the slot sum
+                colsum = rsplit.clone()
+                work_cs = dist.all_reduce(colsum, op=dist.ReduceOp.SUM, async_op=True)
+                finish_dt = _text_grad_scatter(eng, ws, gmat, shape, coef, ctx.scale, gout, rank, d_txt,
+                                               dot_slots=ws.dot_slots)
+                eng.gmat_gemm(False, gmat, shape, ws.txt_all, coef, ctx.scale, gout, ws.scratch, d_img)
+                finish_dt()
+                work_cs.wait()
+                ds = ((ws.dot_slots.sum() + gout * ((0.6931471805599453 * 0.5 / n) * (rsplit.sum() - colsum[rank])))
+                      / ctx.scale).reshape(1)
+                ds_done = True
             else:
                 colsum = work_cs = None
                 if need_s:   # column-softmax entropies of my columns live on every rank: W-float all-reduce, async

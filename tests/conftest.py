@@ -59,6 +59,8 @@ class StandInEngine:
 
     name = "cpu-standin"
 
+    exact_g = False     # True: the gradient GEMMs contract a float64 copy of G (sharp checks of scalar formulas)
+
     def __init__(self):
         self.state = {}
         self.calls = []
@@ -194,6 +196,8 @@ class StandInEngine:
         s = float(scale.item())
         go = 1.0 if grad_out is None else float(grad_out.item())
         g = self._gview(gmat, shape).double()
+        if self.exact_g and ("g64", gmat.data_ptr()) in self.state:
+            g = self.state[("g64", gmat.data_ptr())]
         assert feat.shape[0] == (shape.m_rows if transposed else shape.n_cols)
         out = (g.t() if transposed else g) @ feat.double()
         d_out.copy_((coef * s * go * out)[:, :d_out.shape[1]].to(d_out.dtype))
@@ -217,6 +221,7 @@ class StandInEngine:
         g = w_row * p_row + w_col * p_col
         g[idx, idx + shape.label_offset] -= (w_row + w_col)
         self._gview(emat, shape).copy_(g.to(torch.bfloat16))
+        self.state[("g64", emat.data_ptr())] = g
         if msums is not None:
             assert n_per_rank * ranks == shape.n_cols and tuple(msums.shape[1:]) == (2, ranks)
             msums.zero_()
@@ -227,6 +232,31 @@ class StandInEngine:
                 cols = slice(r * n_per_rank, (r + 1) * n_per_rank)
                 msums[0, r] = float((w_row * p_row[:, cols] * lp_row[:, cols]).sum())
                 msums[1, r] = float((w_col * p_col[:, cols] * lp_col[:, cols]).sum())
+
+    # ---- MRCLIP_DS=fwd: forward-side row sums for d logit_scale ---------------------------------
+    def fwd_row_ent_ok(self, m_rows, n_cols, n_per_rank):
+        return n_cols % n_per_rank == 0
+
+    def clip_fwd_tiles_eu(self, a_rows, b_all, shape, scale, col_begin, col_end, ws, emat):
+        self.clip_fwd_tiles_e(a_rows, b_all, shape, scale, col_begin, col_end, ws, emat)
+        self.calls[-1] = "clip_fwd_tiles_eu"
+        self.state[("u", ws.data_ptr())] = self.state[ws.data_ptr()]["z"] * LOG2E
+
+    def row_ent_split(self, shape, ws, lse2_row, n_per_rank, ranks, out_slots):
+        self.calls.append("row_ent_split")
+        t2 = self.state.pop(("u", ws.data_ptr()))
+        p_row = torch.exp2(t2 - lse2_row[:shape.m_rows].double()[:, None])
+        out_slots.zero_()
+        for q in range(ranks):
+            cols = slice(q * n_per_rank, (q + 1) * n_per_rank)
+            out_slots[q % out_slots.shape[0], 0, q] = float((p_row[:, cols] * t2[:, cols]).sum())
+
+    def sum_slots_dot(self, slots, d_out, feat, dot_slots):
+        self.calls.append("sum_slots_dot")
+        tot = slots.double().sum(0)
+        d_out.copy_(tot.to(d_out.dtype))
+        dot_slots.zero_()
+        dot_slots[0] = float((tot * feat.double()[:, :tot.shape[1]]).sum())
 
     def gmat_gemm_dot(self, transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out, dot_feat, dot_out):
         self.gmat_gemm(transposed, gmat, shape, feat, coef, scale, grad_out, ws, d_out)

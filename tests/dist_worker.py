@@ -71,6 +71,30 @@ def main():
                 failures.append((name, backend, rank, bad, errs))
             if rank == 0:
                 print(f"{name:32s} {backend:9s} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+    if os.environ.get("MRCLIP_TEST_FWDDS") == "1":
+        # opt-in (not validated on hardware yet): MRCLIP_DS=fwd against the entropy path on the same inputs, at a size
+        # where <dT_r, T_r> averages the bf16 rounding of G out (n*N >= 2^22)
+        os.environ["MRCLIP_BWD"], os.environ["MRCLIP_RS"], os.environ["MRCLIP_AG"] = "emat", "push", "push"
+        N, D = 16384, 384
+        n = N // world
+        g = torch.Generator().manual_seed(77)
+        img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+        txt = torch.nn.functional.normalize(0.4 * img + 0.6 * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
+        res = {}
+        for mode in ("entropy", "fwd"):
+            os.environ["MRCLIP_DS"] = mode
+            i = img[rank * n:(rank + 1) * n].bfloat16().to(dev).requires_grad_(True)
+            t = txt[rank * n:(rank + 1) * n].bfloat16().to(dev).requires_grad_(True)
+            s = torch.tensor(30.0, device=dev, requires_grad=True)
+            mod = ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+            (mod(i, t, s) * 3.0).backward()
+            res[mode] = (s.grad.item(), i.grad.float().cpu().numpy(), t.grad.float().cpu().numpy())
+        os.environ["MRCLIP_DS"] = "entropy"
+        errs = dict(d_scale=abs(res["fwd"][0] - res["entropy"][0]) / abs(res["entropy"][0]),
+                    d_image=rel_err(res["fwd"][1], res["entropy"][1]), d_text=rel_err(res["fwd"][2], res["entropy"][2]))
+        print(f"rank {rank} MRCLIP_DS=fwd vs entropy: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+        if errs["d_scale"] > 2e-3 or errs["d_image"] > 1e-6 or errs["d_text"] > 1e-6:
+            failures.append(("fwd_ds", "emat", rank, list(errs), errs))
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     for f in failures:

@@ -345,3 +345,45 @@ def test_gather_with_tokens_and_materialised_multipositive_gloo():
         assert np.array_equal(out["gi"], case["image"])
         assert abs(out["loss"] - float(ref["loss"])) <= 1e-5 * abs(float(ref["loss"]))
         assert rel_err(out["d_image"], ref["d_image"]) <= 1e-5 and rel_err(out["d_text"], ref["d_text"]) <= 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# MRCLIP_DS=fwd (opt-in): d logit_scale of the multi-rank local loss from forward-side row sums and <dT_r, T_r>
+# ------------------------------------------------------------------------------------------------
+def _fwd_ds_worker(rank, world, init_file, name, exact, ret):
+    os.environ["MRCLIP_BWD"] = "emat"
+    os.environ["MRCLIP_DS"] = "fwd"
+    import mrclip_b200.loss as L
+    L._FWD_DS_MIN_PAIRS = 0          # the fixtures are far below the production threshold
+    eng = StandInEngine()
+    eng.exact_g = exact
+    mrclip_b200.set_engine(eng)
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        case = load_golden(name)
+        out = _run_rank(case, rank, world, case["image"], case["text"])
+        out["calls"] = list(eng.calls)
+        ret[rank] = out
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name,exact", [("clip_w2_ll1_gg1", True), ("clip_w4_ll1_gg1", True), ("clip_w4_ll1_gg1", False),
+                                        ("clip_w2_ll0_gg1", True)])
+def test_forward_side_d_scale_matches_reference(name, exact):
+    """s dL_r/ds = <dT_r, T_r> + ln2/(2n) (R2(r,*) - R2(*,r)) reproduces the reference's per-rank d logit_scale; with
+    G rounded to bf16 (exact=False) only up to the noise a 16..32-row fixture cannot average out."""
+    case = load_golden(name)
+    world = case["world"]
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td:
+        mp.spawn(_fwd_ds_worker, args=(world, os.path.join(td, "init"), name, exact, ret), nprocs=world, join=True)
+    local = bool(case["meta"]["local_loss"])
+    for r in range(world):
+        _compare(ret[r], case["ranks"][r], "clip", grad_tol=GRAD_TOL if exact else 5e-3,
+                 scale_tol=1e-4 if (exact or not local) else 5e-2)
+        used = ret[r]["calls"]
+        assert ("clip_fwd_tiles_eu" in used and "row_ent_split" in used) == local      # global-loss modes keep the entropy path
+        assert ("clip_fwd_tiles_e" in used) == (not local)
