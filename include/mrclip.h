@@ -194,6 +194,16 @@ int mrclip_row_ent_split(mrclip_shape shape, void* ws, const float* lse2_row, in
 int mrclip_sum_slots_dot(const float* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
                          const void* feat, long feat_ld, float* dot_slots, void* stream);
 
+/* Fused GEMM -> reduce-scatter with a bf16 payload (MRCLIP_PUSH_DTYPE=bf16, NOT validated on hardware yet, default off):
+ * mrclip_gmat_gemm_push whose peer_bufs are bf16 [W, n_per_rank, d] receive buffers (two accumulator chunks per
+ * 128-byte row piece: half the NVLink bytes of loss.py's all_gather backward), and the owner-side slot sum over bf16
+ * slots, optionally with the <dT_r, T_r> dot of mrclip_sum_slots_dot (feat and dot_slots both NULL or both set). */
+int mrclip_gmat_gemm_push_bf16(const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                               const float* scale, const float* grad_out, void* ws, const unsigned long long* peer_bufs,
+                               int n_per_rank, int my_rank, void* stream);
+int mrclip_sum_slots_bf16(const void* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                          const void* feat, long feat_ld, float* dot_slots, void* stream);
+
 /* SigLipLoss has no normaliser: its forward can store G = sigmoid(z) - [j==label_i] directly (then both
  * gradients are plain mrclip_gmat_gemm calls) and leaves the d_scale / d_bias partial sums in ws. */
 int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,

@@ -57,6 +57,8 @@ SIGNATURES = {
     "mrclip_clip_fwd_tiles_eu": (_I, [_P, _P, Shape, _I, _P, _I, _I, _P, _P, _P]),
     "mrclip_row_ent_split": (_I, [Shape, _P, _P, _I, _I, _P, _P]),
     "mrclip_sum_slots_dot": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
+    "mrclip_gmat_gemm_push_bf16": (_I, [_P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _I, _P]),
+    "mrclip_sum_slots_bf16": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
     "mrclip_launch_count": (_L, []),
 }
 

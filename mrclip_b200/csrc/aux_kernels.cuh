@@ -574,6 +574,32 @@ __global__ void sum_slots_dot_kernel(const float* __restrict__ slots, int nslots
   }
 }
 
+// the owner's side of the fused reduce-scatter with a bf16 payload; optionally <out, feat> into dot_out[blockIdx.x % 64]
+__global__ void sum_slots_bf16_kernel(const __nv_bfloat16* __restrict__ slots, int nslots, int rows, int d,
+                                      void* __restrict__ out, int out_dtype, long out_ld,
+                                      const __nv_bfloat16* __restrict__ feat, long feat_ld, float* __restrict__ dot_out) {
+  const long total = (long)rows * d;
+  float dot = 0.f;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < nslots; ++k) a += __bfloat162float(slots[k * total + i]);
+    const long r = i / d;
+    const int c = (int)(i - r * d);
+    store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
+    if (feat != nullptr) dot = fmaf(a, __bfloat162float(feat[r * feat_ld + c]), dot);
+  }
+  if (feat == nullptr) return;     // grid-uniform
+  dot = warp_sum(dot);
+  __shared__ float part[32];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) atomicAdd(dot_out + (blockIdx.x & 63), v);
+  }
+}
+
 // R2(me, q) = sum over my rows i and the columns j owned by rank q of Prow_ij * S2_ij, from the forward's per-slot
 // (max2, sum) and u partials (tile_kernel.cuh, MODE_FWDEU): out[(blockIdx.x % 64) * 2 * ranks + q] += block sum.
 // A slot is one half of a column chunk; slots_per_rank consecutive slots belong to one owner.

@@ -21,15 +21,17 @@ constexpr int kG2Bars = 2 * 6 + 4;
 // PUSH (fused reduce-scatter): one ring stage is traded for a 32 x 32 fp32 staging tile per epilogue warp (rows
 // padded to 144 B against bank conflicts), from which every lane sends its row as one 128-byte bulk copy -- peer
 // memory over NVLink wants full-line packets, 16-byte stores from the registers reached a fraction of the link rate
+// PUSH = 2 (MRCLIP_PUSH_DTYPE=bf16, not validated on hardware yet): the same with a bf16 payload -- two 32-column
+// accumulator chunks per 128-byte row piece, half the NVLink bytes of the text-gradient exchange.
 constexpr int kG2PushRowBytes = 144;
-template <bool PUSH> struct G2Cfg {
+template <int PUSH> struct G2Cfg {
   static constexpr int kStages = PUSH ? 5 : 6;
   static constexpr int kStagingBytes = PUSH ? kEpiWarps * 32 * kG2PushRowBytes : 0;
   static constexpr int kSmemBytes = kStages * kG2StageBytes + kStagingBytes + kG2Bars * 8 + 16 + 1024;
 };
 
 // GemmParams::num_rb counts 256-row pair blocks here.
-template <bool A_MN, bool PUSH>
+template <bool A_MN, int PUSH>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const GemmParams p) {
@@ -175,9 +177,50 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (p.grad_out != nullptr) mul *= __ldg(p.grad_out);
       }
 #pragma unroll 1
-      for (int c0 = h * 128; c0 < (int)(h + 1) * 128; c0 += 32) {
+      for (int c0 = h * 128; c0 < (int)(h + 1) * 128; c0 += (PUSH == 2 ? 64 : 32)) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0, r);
+        if (PUSH == 2) {
+          // bf16 payload: 64 accumulator columns -> one 128-byte row piece in the owner's bf16 receive slot
+          uint32_t r2[32];
+          tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0 + 32, r2);
+          tmem_ld_wait();
+          const int col = dt * kGemmBN + c0;
+          const int qo = grow / p.peer_n, lrow = grow - qo * p.peer_n;
+          __nv_bfloat16* orow = nullptr;
+          if (grow < p.m_rows)
+            orow = reinterpret_cast<__nv_bfloat16*>(__ldg(p.peer + qo)) + ((size_t)p.peer_rank * p.peer_n + lrow) * p.out_ld;
+          if (col + 64 <= p.d_valid && (p.out_ld & 7) == 0) {
+            const uint32_t my_row = staging_base + ((warp - 2) * 32 + lane) * kG2PushRowBytes;
+            bulk_wait_read0();                     // this lane's previous row piece has left the staging tile
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o, o2;
+              o.x = pack_bf16x2(__uint_as_float(r[8 * j]) * mul, __uint_as_float(r[8 * j + 1]) * mul);
+              o.y = pack_bf16x2(__uint_as_float(r[8 * j + 2]) * mul, __uint_as_float(r[8 * j + 3]) * mul);
+              o.z = pack_bf16x2(__uint_as_float(r[8 * j + 4]) * mul, __uint_as_float(r[8 * j + 5]) * mul);
+              o.w = pack_bf16x2(__uint_as_float(r[8 * j + 6]) * mul, __uint_as_float(r[8 * j + 7]) * mul);
+              o2.x = pack_bf16x2(__uint_as_float(r2[8 * j]) * mul, __uint_as_float(r2[8 * j + 1]) * mul);
+              o2.y = pack_bf16x2(__uint_as_float(r2[8 * j + 2]) * mul, __uint_as_float(r2[8 * j + 3]) * mul);
+              o2.z = pack_bf16x2(__uint_as_float(r2[8 * j + 4]) * mul, __uint_as_float(r2[8 * j + 5]) * mul);
+              o2.w = pack_bf16x2(__uint_as_float(r2[8 * j + 6]) * mul, __uint_as_float(r2[8 * j + 7]) * mul);
+              sts_u4(my_row + 16 * j, o);
+              sts_u4(my_row + 64 + 16 * j, o2);
+            }
+            fence_proxy_async_smem();
+            if (orow != nullptr) {
+              bulk_store(orow + col, my_row, 128);
+              bulk_commit();
+            }
+          } else if (orow != nullptr) {            // ragged D: element stores
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (col + j < p.d_valid) orow[col + j] = __float2bfloat16(__uint_as_float(r[j]) * mul);
+              if (col + 32 + j < p.d_valid) orow[col + 32 + j] = __float2bfloat16(__uint_as_float(r2[j]) * mul);
+            }
+          }
+          continue;
+        }
         tmem_ld_wait();
         if (PUSH && p.peer != nullptr && dt * kGemmBN + c0 + 32 <= p.d_valid && (p.out_ld & 3) == 0) {
           // push epilogue: scale into the warp's staging tile, then one 128-byte bulk copy per row to the owner

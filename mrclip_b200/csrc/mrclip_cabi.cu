@@ -397,7 +397,7 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
   return 0;
 }
 
-template <bool A_MN, bool PUSH>
+template <bool A_MN, int PUSH>
 int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
   auto kern = gemm2_kernel<A_MN, PUSH>;
   constexpr int kG2SmemBytes = G2Cfg<PUSH>::kSmemBytes;
@@ -417,7 +417,11 @@ int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams&
 
 template <bool A_MN>
 int launch_gemm(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  if (gemm_pairs()) return p.peer ? launch_gemm2<A_MN, true>(ma, mb, p, st) : launch_gemm2<A_MN, false>(ma, mb, p, st);
+  if (p.peer && p.out_dtype == DT_BF16) {   // bf16 push payload: CTA-pair kernel only
+    if (!gemm_pairs()) return fail(-1, "the bf16 push epilogue needs the CTA-pair GEMM (MRCLIP_GEMM_CTA=2)");
+    return launch_gemm2<A_MN, 2>(ma, mb, p, st);
+  }
+  if (gemm_pairs()) return p.peer ? launch_gemm2<A_MN, 1>(ma, mb, p, st) : launch_gemm2<A_MN, 0>(ma, mb, p, st);
   auto kern = gemm_kernel<A_MN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -890,6 +894,42 @@ int mrclip_gmat_gemm_push(const void* gmat, mrclip_shape shape, const void* feat
   // d_out only marks the epilogue as direct; rows are routed through peer_bufs (dense fp32, leading dim d)
   return run_gmat_gemm(true, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out, ws,
                        const_cast<unsigned long long*>(peer_bufs), MRCLIP_DT_F32, shape.d, xf, (cudaStream_t)stream);
+}
+
+/* mrclip_gmat_gemm_push with a bf16 payload: peer_bufs are bf16 [W, n_per_rank, d] receive buffers (MRCLIP_PUSH_DTYPE=bf16,
+ * not validated on hardware yet) */
+int mrclip_gmat_gemm_push_bf16(const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
+                               const float* scale, const float* grad_out, void* ws, const unsigned long long* peer_bufs,
+                               int n_per_rank, int my_rank, void* stream) {
+  if (int e = check_shape(shape, ld)) return e;
+  if (!peer_bufs || n_per_rank <= 0 || shape.n_cols % n_per_rank != 0 || my_rank < 0 ||
+      my_rank >= shape.n_cols / n_per_rank)
+    return fail(-1, "gmat_gemm_push_bf16: bad peer layout (n_per_rank=%d, rank=%d, n_cols=%d)", n_per_rank, my_rank, shape.n_cols);
+  DotArgs xf;
+  xf.peer = peer_bufs;
+  xf.peer_n = n_per_rank;
+  xf.peer_rank = my_rank;
+  return run_gmat_gemm(true, gmat, shape.m_rows, shape.n_cols, feat, shape.d, ld, coef, scale, grad_out, ws,
+                       const_cast<unsigned long long*>(peer_bufs), MRCLIP_DT_BF16, shape.d, xf, (cudaStream_t)stream);
+}
+
+/* mrclip_sum_slots / mrclip_sum_slots_dot over bf16 slots (feat / dot_slots optional) */
+int mrclip_sum_slots_bf16(const void* slots, int nslots, int rows, int d, void* out, int out_dtype, long out_ld,
+                          const void* feat, long feat_ld, float* dot_slots, void* stream) {
+  if (!slots || !out || nslots <= 0 || rows <= 0 || d <= 0) return fail(-1, "sum_slots_bf16: bad arguments");
+  if ((feat == nullptr) != (dot_slots == nullptr) || (feat && feat_ld < d)) return fail(-1, "sum_slots_bf16: feat and dot_slots go together");
+  if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dot_slots) CUDA_TRY(cudaMemsetAsync(dot_slots, 0, 64 * sizeof(float), st));
+  const long total = (long)rows * d;
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  sum_slots_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(slots), nslots, rows, d, out,
+                                                     out_dtype, out_ld, reinterpret_cast<const __nv_bfloat16*>(feat),
+                                                     feat_ld, dot_slots);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
 }
 
 int mrclip_push_copy(const void* src, size_t bytes, const unsigned long long* peer_bufs, int ranks, size_t dst_offset,

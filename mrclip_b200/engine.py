@@ -157,12 +157,21 @@ class CudaEngine:
                                                   d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0),
                                                   _ptr(dot_feat), _ptr(dot_out), self._stream()))
 
-    def gmat_gemm_push(self, gmat, shape, feat, coef, scale, grad_out, ws, peer_ptrs, n_per_rank, my_rank):
+    def gmat_gemm_push(self, gmat, shape, feat, coef, scale, grad_out, ws, peer_ptrs, n_per_rank, my_rank, bf16=False):
         """G^T . A with the epilogue scattering row block q into rank q's receive buffer (peer_ptrs: int64 device
-        tensor of NVLink-mapped addresses), slot my_rank."""
-        _cabi.check(self.lib.mrclip_gmat_gemm_push(gmat.data_ptr(), shape, feat.data_ptr(), feat.shape[1], coef,
-                                                   scale.data_ptr(), _ptr(grad_out), ws.data_ptr(),
-                                                   peer_ptrs.data_ptr(), n_per_rank, my_rank, self._stream()))
+        tensor of NVLink-mapped addresses), slot my_rank.  bf16: the receive buffers are bf16 (MRCLIP_PUSH_DTYPE=bf16)."""
+        fn = self.lib.mrclip_gmat_gemm_push_bf16 if bf16 else self.lib.mrclip_gmat_gemm_push
+        _cabi.check(fn(gmat.data_ptr(), shape, feat.data_ptr(), feat.shape[1], coef, scale.data_ptr(), _ptr(grad_out),
+                       ws.data_ptr(), peer_ptrs.data_ptr(), n_per_rank, my_rank, self._stream()))
+
+    def sum_slots_bf16(self, slots, d_out, feat=None, dot_slots=None):
+        """sum_slots / sum_slots_dot over bf16 slots."""
+        assert slots.dtype == torch.bfloat16 and slots.is_contiguous() and slots.dim() == 3
+        assert (feat is None) == (dot_slots is None)
+        _cabi.check(self.lib.mrclip_sum_slots_bf16(slots.data_ptr(), slots.shape[0], slots.shape[1], slots.shape[2],
+                                                   d_out.data_ptr(), _DT[d_out.dtype], d_out.stride(0), _ptr(feat),
+                                                   0 if feat is None else feat.stride(0), _ptr(dot_slots),
+                                                   self._stream()))
 
     def push_copy(self, src, peer_ptrs, dst_offset_bytes, skip_rank):
         """copy the contiguous tensor src into every peer's buffer at dst_offset_bytes (all-gather by NVLink stores)"""

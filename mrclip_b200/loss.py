@@ -196,7 +196,9 @@ class _Workspace:
             if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "push").lower() != "nccl":
                 try:
                     import torch.distributed._symmetric_memory as symm_mem
-                    recv = symm_mem.empty((self.world, self.n, self.d), dtype=torch.float32, device=self.img_all.device)
+                    # MRCLIP_PUSH_DTYPE=bf16 (opt-in, not validated on hardware yet): half the NVLink bytes
+                    pdt = torch.bfloat16 if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" else torch.float32
+                    recv = symm_mem.empty((self.world, self.n, self.d), dtype=pdt, device=self.img_all.device)
                     hdl = symm_mem.rendezvous(recv, dist.group.WORLD)
                     ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.img_all.device)
                     self.push = (recv, ptrs, hdl)
@@ -350,6 +352,13 @@ def _text_grad_scatter(eng, ws, gmat, shape, coef, scale, gout, rank, d_txt, dot
     push = ws.push_buffers(rank)
     if push is not None:
         recv, ptrs, hdl = push
+        if recv.dtype == torch.bfloat16:
+            eng.gmat_gemm_push(gmat, shape, ws.img_all[rows], coef, scale, gout, ws.scratch, ptrs, n, rank, bf16=True)
+
+            def finish_bf16():
+                hdl.barrier()
+                eng.sum_slots_bf16(recv, d_txt, None if dot_slots is None else ws.txt_all[rows], dot_slots)
+            return finish_bf16
         eng.gmat_gemm_push(gmat, shape, ws.img_all[rows], coef, scale, gout, ws.scratch, ptrs, n, rank)
 
         def finish():

@@ -31,9 +31,13 @@ def main():
         m = case["meta"]
         assert case["world"] == world, (name, case["world"], world)
         # emat: collectives over NVLink peer memory (push all-gathers, GEMM push epilogue); emat-nccl: the same through NCCL
-        for backend in ("emat", "emat-nccl", "gmat", "fused"):
+        backends = ("emat", "emat-nccl", "gmat", "fused")
+        if os.environ.get("MRCLIP_TEST_PUSHBF16") == "1":     # opt-in: bf16 payload of the fused GEMM -> reduce-scatter
+            backends += ("emat-bf16",)
+        for backend in backends:
             os.environ["MRCLIP_BWD"] = backend.split("-")[0]
             os.environ["MRCLIP_RS"] = "nccl" if backend.endswith("-nccl") else "push"
+            os.environ["MRCLIP_PUSH_DTYPE"] = "bf16" if backend.endswith("-bf16") else "fp32"
             os.environ["MRCLIP_AG"] = os.environ["MRCLIP_RS"]      # all-gathers: NCCL or peer stores, likewise
             n = case["image"].shape[0] // world
             rows = slice(rank * n, (rank + 1) * n)
@@ -42,7 +46,7 @@ def main():
             s = torch.tensor(float(m["scale"]), device=dev, requires_grad=True)
             ref = case["ranks"][rank]
             if m["kind"] == "mpos":
-                if backend not in ("emat", "emat-nccl"):
+                if backend not in ("emat", "emat-nccl", "emat-bf16"):
                     continue        # the multi-positive loss always runs the E-block pipeline
                 mod = MultiPositiveClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
                                             rank=rank, world_size=world)
