@@ -255,6 +255,7 @@ def run_ours(args):
     # launching stream; the roofline is quoted for the costliest op that carries algorithmic flops
     ALG_OPS = {"clip_fwd_tiles": "tile_kernel<MODE_FWD> (S = A.B^T tiles + online LSE, 2nND flop)",
                "clip_fwd_tiles_e": "tile_kernel<MODE_FWDE> (S = A.B^T tiles + online LSE + bf16 E block out, 2nND flop)",
+               "clip_fwd_tiles_eu": "tile_kernel<MODE_FWDEU> (FWDE + per-chunk row sums for d logit_scale, 2nND flop)",
                "siglip_fwd_e": "tile_kernel<MODE_FWDE, SIGLIP> (S tiles + softplus sum + bf16 G block out, 2nND flop)",
                "gmat_gemm": "gemm2_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
                "gmat_gemm_dot": "gemm2_kernel (dA = G.B from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
@@ -262,7 +263,7 @@ def run_ours(args):
                "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)"}
     TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "siglip_fwd_e", "clip_fwd_reduce", "lse2_merge",
              "clip_loss", "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "gmat_gemm_push", "push_copy",
-             "sum_slots", "clip_bwd"]
+             "sum_slots", "clip_bwd", "clip_fwd_tiles_eu", "row_ent_split", "sum_slots_dot", "sum_slots_bf16"]
     ev = {k: [] for k in TIMED}
     originals = {k: getattr(eng, k) for k in TIMED}
 
@@ -381,6 +382,8 @@ def run_ours(args):
             "gpu_launches": launches,
             "op_ms_per_step": {k: round(v, 4) for k, v in per_op_ms.items()},
             "backward_backend": os.environ.get("MRCLIP_BWD", "auto"),
+            "knobs": {k: os.environ[k] for k in ("MRCLIP_DS", "MRCLIP_PUSH_DTYPE", "MRCLIP_AG", "MRCLIP_RS", "MRCLIP_GEMM_CTA")
+                      if k in os.environ},
             "clocks": clocks,
         }
         if cpu_base is not None:
