@@ -46,7 +46,7 @@ def test_captured_step_replays_the_eager_step(kind, n, d):
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     gr = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(gr, stream=side):
+    with torch.cuda.graph(gr, stream=side, capture_error_mode="thread_local"):
         g_loss = step()
     static = [p.grad for p in params]
     # new inputs through the static tensors: the replay must follow them
