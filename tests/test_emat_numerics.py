@@ -97,3 +97,43 @@ def test_guard_condition_fires_when_a_reference_dwarfs_its_band():
     txt[0] = img[0]                         # S2_00 = 144, every other logit of the band is ~ +-15
     out = emat_pipeline(img, txt, scale)
     assert out["flag"]
+
+
+def test_forward_side_row_sums_online_merge():
+    """MODE_FWDEU's bookkeeping (tile_kernel.cuh) and row_ent_split_kernel, restated in fp32: per 64-column sub-tile
+    u += sum e*(S2 - c) + c*sum e, merged across sub-tiles with the LSE's rescaling factors, one (m, l, u) triple per
+    (row, column-chunk half); the split by column owner then gives R2(me, q) = sum_{i, j in q} Prow_ij * S2_ij."""
+    n, N, d, scale, ranks = 128, 1024, 64, 100.0, 4
+    img, txt = _feats(N, d, 3, 0.5)
+    s2 = ((scale * LOG2E) * (img[:n] @ txt.T)).astype(np.float32)
+    f32 = np.float32
+    slot_cols = 128                                    # one chunk half (tiles_per_chunk = 1)
+    slots = N // slot_cols
+    m = np.full((slots, n), -np.inf, f32)
+    l = np.zeros((slots, n), f32)
+    u = np.zeros((slots, n), f32)
+    for s in range(slots):
+        for sub in range(slot_cols // 64):
+            cols = slice(s * slot_cols + sub * 64, s * slot_cols + sub * 64 + 64)
+            for b in range(0, n, 32):
+                blk = s2[b:b + 32, cols]
+                c = f32(blk.max())
+                t = (blk - c).astype(f32)
+                e = np.exp2(t).astype(f32)
+                rowsum, row_t = e.sum(1, dtype=f32), (e * t).sum(1, dtype=f32)
+                mnew = np.maximum(m[s, b:b + 32], c)
+                f_old, f_new = np.exp2(m[s, b:b + 32] - mnew).astype(f32), np.exp2(c - mnew).astype(f32)
+                l[s, b:b + 32] = l[s, b:b + 32] * f_old + rowsum * f_new
+                u[s, b:b + 32] = u[s, b:b + 32] * f_old + (row_t + c * rowsum) * f_new
+                m[s, b:b + 32] = mnew
+    mx = m.max(0)
+    lse = mx + np.log2((l * np.exp2(m - mx)).sum(0))
+    per = slots // ranks
+    got = np.array([(np.exp2(m[q * per:(q + 1) * per] - lse) * u[q * per:(q + 1) * per]).sum() for q in range(ranks)])
+    s2d = s2.astype(np.float64)
+    lse_ref = np.log2(np.exp2(s2d - s2d.max(1, keepdims=True)).sum(1)) + s2d.max(1)
+    p = np.exp2(s2d - lse_ref[:, None])
+    want = np.array([(p[:, q * (N // ranks):(q + 1) * (N // ranks)] * s2d[:, q * (N // ranks):(q + 1) * (N // ranks)]).sum()
+                     for q in range(ranks)])
+    assert np.abs(lse - lse_ref).max() < 1e-4
+    assert np.abs(got - want).max() <= 1e-5 * np.abs(want).max()
