@@ -185,7 +185,8 @@ int mrclip_sum_slots(const float* slots, int nslots, int rows, int d, void* out,
  * chunk half in ws; after mrclip_clip_fwd_reduce, mrclip_row_ent_split turns them into R2(me, q) for every owner q
  * (out_slots: float [64][2][ranks], plane 0, summed over the 64 slots by the caller); mrclip_sum_slots_dot is
  * mrclip_sum_slots that also accumulates <dT_r, T_r> (feat: packed bf16 rows of this rank) into dot_slots[64].
- * mrclip_fwd_row_ent_ok: 1 when every column chunk of the forward plan has a single owner. */
+ * mrclip_fwd_row_ent_ok: 1 when every column chunk of the forward plan has a single owner.  The two slot sums of the
+ * staged paths (this one and mrclip_sum_slots_bf16) read four columns per thread and need d % 4 == 0. */
 int mrclip_fwd_row_ent_ok(int m_rows, int n_cols, int n_per_rank);
 int mrclip_clip_fwd_tiles_eu(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const float* scale,
                              int col_begin, int col_end, void* ws, void* emat, void* stream);

@@ -547,46 +547,44 @@ __global__ void sum_slots_kernel(const float* __restrict__ slots, int nslots, in
   }
 }
 
-// sum_slots_kernel that also accumulates <out, feat> (fp32, before the output cast) into dot_out[blockIdx.x % 64]:
-// the text-gradient side of  s dL_r/ds = <dT_r, T_r> + ...  (tile_kernel.cuh, MODE_FWDEU).  feat: packed bf16 [rows, ld].
-__global__ void sum_slots_dot_kernel(const float* __restrict__ slots, int nslots, int rows, int d,
+// Slot sums of the staged paths (MRCLIP_DS=fwd, MRCLIP_PUSH_DTYPE=bf16): out[r, c] = sum_k slots[k][r][c] like
+// sum_slots_kernel, four columns per thread (16-byte loads; requires d % 4 == 0, checked by the caller), slots fp32 or
+// bf16, optionally with <out, feat> (fp32, before the output cast; feat = packed bf16 [rows, feat_ld]) accumulated into
+// dot_out[blockIdx.x % 64] -- the text-gradient side of  s dL_r/ds = <dT_r, T_r> + ...  (tile_kernel.cuh, MODE_FWDEU).
+template <bool SLOTS_BF16>
+__global__ void sum_slots_vec_kernel(const void* __restrict__ slots, int nslots, int rows, int d,
                                      void* __restrict__ out, int out_dtype, long out_ld,
                                      const __nv_bfloat16* __restrict__ feat, long feat_ld, float* __restrict__ dot_out) {
-  const long total = (long)rows * d;
-  const long slot_stride = total;
+  const int dq = d >> 2;
+  const long total4 = (long)rows * dq;
+  const long slot_stride = (long)rows * d;
   float dot = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    float a = 0.f;
-    for (int k = 0; k < nslots; ++k) a += slots[k * slot_stride + i];
-    const long r = i / d;
-    const int c = (int)(i - r * d);
-    store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
-    dot = fmaf(a, __bfloat162float(feat[r * feat_ld + c]), dot);
-  }
-  dot = warp_sum(dot);
-  __shared__ float part[32];
-  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = dot;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float v = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
-    v = warp_sum(v);
-    if (threadIdx.x == 0) atomicAdd(dot_out + (blockIdx.x & 63), v);
-  }
-}
-
-// the owner's side of the fused reduce-scatter with a bf16 payload; optionally <out, feat> into dot_out[blockIdx.x % 64]
-__global__ void sum_slots_bf16_kernel(const __nv_bfloat16* __restrict__ slots, int nslots, int rows, int d,
-                                      void* __restrict__ out, int out_dtype, long out_ld,
-                                      const __nv_bfloat16* __restrict__ feat, long feat_ld, float* __restrict__ dot_out) {
-  const long total = (long)rows * d;
-  float dot = 0.f;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    float a = 0.f;
-    for (int k = 0; k < nslots; ++k) a += __bfloat162float(slots[k * total + i]);
-    const long r = i / d;
-    const int c = (int)(i - r * d);
-    store_from_float(out, out_dtype, (size_t)(r * out_ld + c), a);
-    if (feat != nullptr) dot = fmaf(a, __bfloat162float(feat[r * feat_ld + c]), dot);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / dq;
+    const int c = (int)(i - r * dq) << 2;
+    const long e = r * d + c;
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = 0; k < nslots; ++k) {
+      if (SLOTS_BF16) {
+        const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(slots) + k * slot_stride + e);
+        a[0] += __uint_as_float(v.x << 16);
+        a[1] += __uint_as_float(v.x & 0xffff0000u);
+        a[2] += __uint_as_float(v.y << 16);
+        a[3] += __uint_as_float(v.y & 0xffff0000u);
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(slots) + k * slot_stride + e);
+        a[0] += v.x;
+        a[1] += v.y;
+        a[2] += v.z;
+        a[3] += v.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) store_from_float(out, out_dtype, (size_t)(r * out_ld + c + j), a[j]);
+    if (feat != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dot = fmaf(a[j], __bfloat162float(feat[r * feat_ld + c + j]), dot);
+    }
   }
   if (feat == nullptr) return;     // grid-uniform
   dot = warp_sum(dot);

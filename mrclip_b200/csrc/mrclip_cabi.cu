@@ -788,13 +788,14 @@ int mrclip_sum_slots_dot(const float* slots, int nslots, int rows, int d, void* 
   if (!slots || !out || !feat || !dot_slots || nslots <= 0 || rows <= 0 || d <= 0 || feat_ld < d)
     return fail(-1, "sum_slots_dot: bad arguments");
   if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  if (d % 4 != 0) return fail(-1, "sum_slots_dot: d=%d must be a multiple of 4", d);
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemsetAsync(dot_slots, 0, 64 * sizeof(float), st));
-  const long total = (long)rows * d;
+  const long total = (long)rows * (d / 4);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
-  sum_slots_dot_kernel<<<(int)blocks, 256, 0, st>>>(slots, nslots, rows, d, out, out_dtype, out_ld,
-                                                    reinterpret_cast<const __nv_bfloat16*>(feat), feat_ld, dot_slots);
+  sum_slots_vec_kernel<false><<<(int)blocks, 256, 0, st>>>(slots, nslots, rows, d, out, out_dtype, out_ld,
+                                                           reinterpret_cast<const __nv_bfloat16*>(feat), feat_ld, dot_slots);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
@@ -919,14 +920,14 @@ int mrclip_sum_slots_bf16(const void* slots, int nslots, int rows, int d, void* 
   if (!slots || !out || nslots <= 0 || rows <= 0 || d <= 0) return fail(-1, "sum_slots_bf16: bad arguments");
   if ((feat == nullptr) != (dot_slots == nullptr) || (feat && feat_ld < d)) return fail(-1, "sum_slots_bf16: feat and dot_slots go together");
   if (out_dtype < 0 || out_dtype > 2) return fail(-1, "bad out_dtype %d", out_dtype);
+  if (d % 4 != 0) return fail(-1, "sum_slots_bf16: d=%d must be a multiple of 4", d);
   cudaStream_t st = (cudaStream_t)stream;
   if (dot_slots) CUDA_TRY(cudaMemsetAsync(dot_slots, 0, 64 * sizeof(float), st));
-  const long total = (long)rows * d;
+  const long total = (long)rows * (d / 4);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 16) blocks = 148L * 16;
-  sum_slots_bf16_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(slots), nslots, rows, d, out,
-                                                     out_dtype, out_ld, reinterpret_cast<const __nv_bfloat16*>(feat),
-                                                     feat_ld, dot_slots);
+  sum_slots_vec_kernel<true><<<(int)blocks, 256, 0, st>>>(slots, nslots, rows, d, out, out_dtype, out_ld,
+                                                          reinterpret_cast<const __nv_bfloat16*>(feat), feat_ld, dot_slots);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;

@@ -197,7 +197,9 @@ class _Workspace:
                 try:
                     import torch.distributed._symmetric_memory as symm_mem
                     # MRCLIP_PUSH_DTYPE=bf16 (opt-in, not validated on hardware yet): half the NVLink bytes
-                    pdt = torch.bfloat16 if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" else torch.float32
+                    pdt = torch.float32
+                    if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" and self.d % 8 == 0:
+                        pdt = torch.bfloat16
                     recv = symm_mem.empty((self.world, self.n, self.d), dtype=pdt, device=self.img_all.device)
                     hdl = symm_mem.rendezvous(recv, dist.group.WORLD)
                     ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.img_all.device)
@@ -439,7 +441,7 @@ class _ClipLossFn(torch.autograd.Function):
         ctx.fwd_ds = bool(use_emat and world > 1 and module.local_loss and module.gather_with_grad
                           and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
                           and os.environ.get("MRCLIP_DS", "entropy").lower() == "fwd"
-                          and n * N >= _FWD_DS_MIN_PAIRS and eng.fwd_row_ent_ok(n, N, n))
+                          and n * N >= _FWD_DS_MIN_PAIRS and d % 4 == 0 and eng.fwd_row_ent_ok(n, N, n))
         _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, use_emat,
                      gather_images=not use_emat and any(ctx.needs_input_grad), row_ent=ctx.fwd_ds)
         loss = torch.empty((1,), dtype=torch.float32, device=device)
