@@ -198,13 +198,17 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_issue = {}
+
     def timed(fn, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
         e0.record()
         for _ in range(steps):
             fn()
         e1.record()
+        host_issue["ms"] = (time.perf_counter() - t0) * 1e3 / steps     # host time to ISSUE a step (no sync inside)
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1:
@@ -220,6 +224,7 @@ def run_ours(args):
     launches0 = eng.launch_count()
     total_ms = timed(lambda: step(img_d, txt_d), args.steps)
     launches = eng.launch_count() - launches0
+    host_issue_ms = host_issue["ms"]
     loss_val = float(step(img_d, txt_d).item())
     ms_per_step = total_ms / args.steps
     value = N / (ms_per_step * 1e-3)
@@ -380,6 +385,7 @@ def run_ours(args):
             "e2e": {"value": N / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": e2e_ms},
             "gpu_launches": launches,
+            "host_issue_ms_per_step": host_issue_ms,    # close to ms_per_step => the step is host-bound
             "op_ms_per_step": {k: round(v, 4) for k, v in per_op_ms.items()},
             "backward_backend": os.environ.get("MRCLIP_BWD", "auto"),
             "knobs": {k: os.environ[k] for k in ("MRCLIP_DS", "MRCLIP_PUSH_DTYPE", "MRCLIP_AG", "MRCLIP_RS", "MRCLIP_GEMM_CTA")
