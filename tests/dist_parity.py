@@ -1,0 +1,135 @@
+"""Production-size parity worker: the public modules against the reference's fp32 torch graph, per rank, on real GPUs.
+
+    python tests/dist_parity.py [case ...]                                   # one GPU
+    torchrun --nproc-per-node W tests/dist_parity.py [case ...]             # W GPUs, NCCL + NVLink peer memory
+
+Every rank feeds the same bf16-rounded synthetic features to (a) ``mrclip_b200`` and (b)
+``tests/torch_ref.py`` -- the reference's operators in fp32 with ``torch.distributed.nn.all_gather`` -- and compares
+loss (1e-3), feature gradients (1e-2, norm-wise), d logit_scale / d logit_bias (1e-2) and, for ClipLoss, the labels
+(bit-exact).  Cases are BASELINE.json's configs at full size:
+
+    c3       ClipLoss (T,T)            N=32768 D=768      (configs[2], the headline)
+    c2       ClipLoss all four modes   N=4096  D=512      (configs[1]; (F,T) and (T,T) are the ones it names)
+    c4       SigLipLoss + logit_bias   N=16384 D=768      (configs[3])
+    mpos     MultiPositiveClipLoss     N=8192  D=512      (512 label classes)
+    ragged   ClipLoss (T,T)            n=1000 per rank, D=200 (no tile / vector alignment anywhere)
+
+and each is run over NVLink peer memory (default) and over NCCL collectives (``-nccl``).  Exit code 1 on any mismatch;
+one line per case / backend with the worst error over ranks.
+"""
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch_ref  # noqa: E402
+from mrclip_b200 import ClipLoss, MultiPositiveClipLoss, SigLipLoss  # noqa: E402
+
+CASES = {
+    "c3": dict(kind="clip", N=32768, D=768, scale=14.285714, modes=[(True, True)]),
+    "c2": dict(kind="clip", N=4096, D=512, scale=14.285714, modes=[(False, True), (True, True), (True, False), (False, False)]),
+    "c2s100": dict(kind="clip", N=4096, D=512, scale=100.0, modes=[(True, True)], grad_output=65536.0),
+    "c4": dict(kind="siglip", N=16384, D=768, scale=10.0, bias=-10.0),
+    "mpos": dict(kind="mpos", N=8192, D=512, scale=14.285714, classes=512, delta=0.3),
+    "ragged": dict(kind="clip", n=1000, D=200, scale=30.0, modes=[(True, True), (False, True)]),
+}
+
+
+def features(N, D, seed, device):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
+    txt = torch.nn.functional.normalize(0.5 * img + 0.5 * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
+    return img.bfloat16().to(device), txt.bfloat16().to(device)
+
+
+def main():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    names = [a for a in sys.argv[1:] if not a.startswith("-")] or list(CASES)
+    transports = ["push", "nccl"] if world > 1 else ["local"]
+    failures = 0
+    for name in names:
+        c = CASES[name]
+        N = c["N"] if "N" in c else c["n"] * world
+        if N % world:
+            continue
+        n, D = N // world, c["D"]
+        img, txt = features(N, D, 1234 + len(name) + N, dev)
+        rows = slice(rank * n, (rank + 1) * n)
+        go = float(c.get("grad_output", 1.0))
+        modes = c.get("modes", [(True, True)])
+        for mode in modes:
+            ref = None
+            for tr in transports:
+                os.environ["MRCLIP_RS"] = os.environ["MRCLIP_AG"] = ("nccl" if tr == "nccl" else "push")
+                i = img[rows].clone().requires_grad_(True)
+                t = txt[rows].clone().requires_grad_(True)
+                s = torch.tensor(c["scale"], device=dev, requires_grad=True)
+                ours = {}
+                t0 = time.perf_counter()
+                if c["kind"] == "clip":
+                    ll, gg = mode
+                    mod = ClipLoss(local_loss=ll, gather_with_grad=gg, cache_labels=True, rank=rank, world_size=world)
+                    loss = mod(i, t, s)
+                    if ref is None:
+                        ref = torch_ref.clip_reference(img[rows], txt[rows], c["scale"], ll, gg, rank, world, go)
+                    nl = n if (world > 1 and ll) else N
+                    labels_ok = torch.equal(mod.get_ground_truth(dev, nl), ref["labels"])
+                elif c["kind"] == "siglip":
+                    b = torch.tensor(c["bias"], device=dev, requires_grad=True)
+                    loss = SigLipLoss(rank=rank, world_size=world)(i, t, s, b)
+                    if ref is None:
+                        ref = torch_ref.siglip_reference(img[rows], txt[rows], c["scale"], c["bias"], rank, world, go)
+                    labels_ok = True
+                else:
+                    lab = torch.randint(0, c["classes"], (N,), generator=torch.Generator().manual_seed(7)).to(dev)
+                    mod = MultiPositiveClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
+                    loss = mod(i, t, s, delta=c["delta"], tokenized_texts=lab[rows])
+                    if ref is None:
+                        ref = torch_ref.mpos_reference(img[rows], txt[rows], c["scale"], lab[rows], c["delta"], rank, world, go)
+                    labels_ok = True
+                (loss * go).backward()
+                ours = dict(loss=loss.detach(), d_image=i.grad, d_text=t.grad, d_scale=s.grad)
+                if c["kind"] == "siglip":
+                    ours["d_bias"] = b.grad
+                errs, bad = torch_ref.compare(ours, ref)
+                torch.cuda.synchronize()
+                if not labels_ok:
+                    bad.append("labels")
+                vals = torch.tensor([errs.get(k, 0.0) for k in ("loss", "d_image", "d_text", "d_scale", "d_bias")] +
+                                    [float(len(bad))], device=dev, dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+                failures += int(vals[-1].item() > 0)
+                if bad:
+                    print(f"MISMATCH rank {rank} {name} {mode} {tr}: {bad} {errs}", flush=True)
+                if rank == 0:
+                    tag = f"{name} W={world} N={N} D={D}" + (f" (ll={int(mode[0])},gg={int(mode[1])})" if c["kind"] == "clip" else "")
+                    print(f"{tag:44s} {tr:5s} loss={float(ours['loss']):.6f} worst over ranks: loss={vals[0]:.2e} dI={vals[1]:.2e} "
+                          f"dT={vals[2]:.2e} ds={vals[3]:.2e}" + (f" db={vals[4]:.2e}" if c["kind"] == "siglip" else "") +
+                          f" labels={'exact' if labels_ok else 'WRONG'}  [{'ok' if vals[-1].item() == 0 else 'FAIL'}]", flush=True)
+            del ref
+            torch.cuda.empty_cache()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print("dist_parity:", "FAILED" if failures else "all green", flush=True)
+    sys.exit(1 if failures else 0)
+
+
+if __name__ == "__main__":
+    main()
