@@ -30,7 +30,9 @@ There is no CPU path: tensors must live on an sm_100a device, otherwise the call
 """
 from __future__ import annotations
 
+import functools
 import os
+import weakref
 from typing import Optional
 
 import torch
@@ -172,6 +174,7 @@ class _Workspace:
         self.lse2_col_all = torch.full((self.npad,), float("inf"), dtype=f32, device=device)
         self.diag2 = torch.zeros((n,), dtype=f32, device=device)
         self.in_use = False
+        self.generation = 0            # bumped every time the set is handed out (see _Lease)
         self.transposed = False
         self.gmat = None
         self.dt_partial = None
@@ -194,19 +197,15 @@ class _Workspace:
         if self.push is None:
             self.push = False
             if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "push").lower() != "nccl":
-                try:
-                    import torch.distributed._symmetric_memory as symm_mem
-                    # MRCLIP_PUSH_DTYPE=bf16 (opt-in, not validated on hardware yet): half the NVLink bytes
-                    pdt = torch.float32
-                    if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" and self.d % 8 == 0:
-                        pdt = torch.bfloat16
-                    recv = symm_mem.empty((self.world, self.n, self.d), dtype=pdt, device=self.img_all.device)
-                    hdl = symm_mem.rendezvous(recv, dist.group.WORLD)
-                    ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=self.img_all.device)
+                # MRCLIP_PUSH_DTYPE=bf16: half the NVLink bytes
+                pdt = torch.float32
+                if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" and self.d % 8 == 0:
+                    pdt = torch.bfloat16
+                bufs = _symmetric_alloc([((self.world, self.n, self.d), pdt)], self.img_all.device, self.world,
+                                        "the gradient reduce-scatter")
+                if bufs is not None:
+                    recv, hdl, ptrs = bufs[0]
                     self.push = (recv, ptrs, hdl)
-                except Exception as exc:  # pragma: no cover  (depends on the driver / fabric setup of the box)
-                    import warnings
-                    warnings.warn(f"mrclip_b200: symmetric memory unavailable ({exc}); using NCCL reduce_scatter")
         return self.push or None
 
     def dt_partial_buffer(self):
@@ -216,23 +215,55 @@ class _Workspace:
         return self.dt_partial
 
 
-def _symmetric_buffers(ws, device):
-    """Collective: every rank allocates the same symmetric buffers in the same order.  None when unavailable."""
-    try:
-        import torch.distributed._symmetric_memory as symm_mem
+def _all_ranks_ok(ok, device):
+    """True only when every rank of the default group reports ok.  The peer-memory paths and their NCCL twins issue
+    different collectives, so the choice between them must never be made by one rank alone."""
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(flag.item())
 
-        def make(shape, dtype):
-            t = symm_mem.empty(shape, dtype=dtype, device=device)
+
+def _symmetric_alloc(specs, device, world, what):
+    """Collective: every rank allocates the symmetric (NVLink peer-mapped) tensors ``specs`` = [(shape, dtype), ...] in
+    the same order and maps its peers' copies.  Returns [(tensor, handle, int64 device tensor of every rank's mapped
+    address)] or None -- on EVERY rank -- when any rank could not allocate or map them, or when the module's
+    world_size is not the default process group's (the handles are made on dist.group.WORLD)."""
+    out, err = [], None
+    if dist.get_world_size() != world:
+        err = f"module world_size {world} != default process group size {dist.get_world_size()}"
+    symm_mem = None
+    if err is None:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            tensors = [symm_mem.empty(shape, dtype=dtype, device=device) for shape, dtype in specs]
+        except Exception as exc:  # pragma: no cover  (depends on the driver / fabric setup of the box)
+            err = f"{type(exc).__name__}: {exc}"
+    if not _all_ranks_ok(err is None, device):
+        import warnings
+        warnings.warn(f"mrclip_b200: symmetric memory unavailable for {what} ({err or 'on another rank'}); using NCCL")
+        return None
+    try:
+        for t in tensors:
             hdl = symm_mem.rendezvous(t, dist.group.WORLD)
+            if len(hdl.buffer_ptrs) != world:
+                raise RuntimeError(f"{len(hdl.buffer_ptrs)} mapped peers for world_size {world}")
             ptrs = torch.tensor([int(p) for p in hdl.buffer_ptrs], dtype=torch.int64, device=device)
             t.zero_()
-            return t, hdl, ptrs
-        return {"txt": [make((ws.N, ws.ld), torch.bfloat16) for _ in range(2)],
-                "stats": make((ws.world, 3, ws.N), torch.float32)}
-    except Exception as exc:  # pragma: no cover  (depends on the driver / fabric setup of the box)
+            out.append((t, hdl, ptrs))
+    except Exception as exc:  # pragma: no cover
+        err = f"{type(exc).__name__}: {exc}"
+    if not _all_ranks_ok(err is None, device):
         import warnings
-        warnings.warn(f"mrclip_b200: symmetric memory unavailable ({exc}); using NCCL all-gathers")
+        warnings.warn(f"mrclip_b200: symmetric memory rendezvous failed for {what} ({err or 'on another rank'}); using NCCL")
         return None
+    return out
+
+
+def _symmetric_buffers(ws, device):
+    """Collective: two text buffers (alternated per step) and the statistics block.  None when unavailable."""
+    bufs = _symmetric_alloc([((ws.N, ws.ld), torch.bfloat16), ((ws.N, ws.ld), torch.bfloat16),
+                             ((ws.world, 3, ws.N), torch.float32)], device, ws.world, "the all-gathers")
+    return None if bufs is None else {"txt": bufs[:2], "stats": bufs[2]}
 
 
 def _backend(eng, ws):
@@ -252,30 +283,66 @@ def _use_gmat(eng, ws):
     return _backend(eng, ws) in ("gmat", "emat")
 
 
+class _Lease:
+    """One hand-out of a workspace, owned by the autograd ctx of the forward that took it.  The set goes back to the
+    pool when backward has consumed it or -- through __del__ -- when the graph is dropped without a backward (skipped
+    step, exception, loss only logged), so a leaked ctx can never pin an n x N block for good.  A second backward
+    through the same graph (retain_graph=True) finds the lease spent: backward rewrites the saved E block in place,
+    so the state it needs no longer exists."""
+    __slots__ = ("ws", "gen", "spent", "__weakref__")
+
+    def __init__(self, ws):
+        self.ws, self.gen, self.spent = ws, ws.generation, False
+
+    def check(self):
+        if self.spent or self.ws.generation != self.gen:
+            raise RuntimeError("mrclip_b200: backward through this loss a second time -- the saved exponentials were "
+                               "consumed (rewritten in place) by the first backward; call forward again "
+                               "(retain_graph=True is not supported by the fused loss)")
+
+    def release(self):
+        if not self.spent:
+            self.spent = True
+            if self.ws.generation == self.gen:
+                self.ws.in_use = False
+
+    def __del__(self):
+        self.release()
+
+
 class _WorkspacePool:
-    """Per-module cache keyed by (device, n, world, d); a set is handed out once until backward returns it."""
+    """Per-module cache keyed by (device, n, world, d); a set is handed out once until its lease ends.  At most
+    4 sets per key and MRCLIP_POOL_KEYS (8) keys are kept: ragged batch sizes evict the least recently used idle key
+    instead of growing without bound."""
 
     def __init__(self):
-        self._free = {}
+        self._free = {}          # key -> list of workspaces; dict order = least recently used first
 
     def take(self, eng, device, n, world, d):
         key = (str(device), n, world, d)
-        lst = self._free.setdefault(key, [])
-        for w in lst:
-            if not w.in_use:
-                w.in_use = True
-                w.transposed = False
-                w.has_emat = False
-                return w
-        w = _Workspace(eng, device, n, world, d)
+        lst = self._free.pop(key, [])
+        self._free[key] = lst    # most recently used
+        w = next((x for x in lst if not x.in_use), None)
+        if w is None:
+            w = _Workspace(eng, device, n, world, d)
+            if len(lst) < 4:
+                lst.append(w)
+            max_keys = int(os.environ.get("MRCLIP_POOL_KEYS", "8"))
+            for old in [k for k in self._free if k != key]:
+                if len(self._free) <= max_keys:
+                    break
+                if not any(x.in_use for x in self._free[old]):
+                    del self._free[old]
         w.in_use = True
-        if len(lst) < 4:
-            lst.append(w)
+        w.generation += 1
+        w.transposed = False
+        w.has_emat = False
         return w
 
     @staticmethod
-    def give_back(w):
-        w.in_use = False
+    def lease(w):
+        return _Lease(w)
+
 
 
 def _scalar_f32(x, device):
@@ -285,6 +352,8 @@ def _scalar_f32(x, device):
 
 
 def _check_inputs(image_features, text_features):
+    if not (torch.is_tensor(image_features) and torch.is_tensor(text_features)):
+        raise TypeError("image_features and text_features must be tensors")
     if image_features.dim() != 2 or image_features.shape != text_features.shape:
         raise ValueError(f"expected two [n, D] feature matrices of equal shape, got {tuple(image_features.shape)} "
                          f"and {tuple(text_features.shape)}")
@@ -292,6 +361,45 @@ def _check_inputs(image_features, text_features):
         raise TypeError(f"unsupported feature dtype {image_features.dtype}")
     if image_features.shape[0] == 0:
         raise ValueError("empty batch")
+    if _engine_override is None:
+        # the kernels take raw device pointers: anything that is not on one sm_100a GPU would fault inside the launch
+        if not (image_features.is_cuda and text_features.is_cuda):
+            raise RuntimeError("mrclip_b200 has no CPU path: features must live on a B200 (sm_100a) device, got "
+                               f"{image_features.device} / {text_features.device}")
+        if image_features.device != text_features.device:
+            raise RuntimeError(f"features on different devices: {image_features.device} vs {text_features.device}")
+        if torch.cuda.get_device_capability(image_features.device)[0] != 10:
+            raise RuntimeError(f"mrclip_b200 kernels are built for sm_100a only; {image_features.device} is "
+                               f"sm_{''.join(map(str, torch.cuda.get_device_capability(image_features.device)))}")
+
+
+def _scoped(fn):
+    """forward(ctx, image_features, ...) / backward(ctx, grad) with the features' device current (see _on_device)."""
+    @functools.wraps(fn)
+    def inner(ctx, first, *rest):
+        if fn.__name__ == "forward":
+            _check_inputs(first, rest[0])
+        device = first.device if fn.__name__ == "forward" else ctx.ws.img_all.device
+        with _on_device(device):
+            return fn(ctx, first, *rest)
+    return inner
+
+
+class _on_device:
+    """Runs the block with the features' GPU current, so that the stream handed to the C ABI (the current stream of the
+    current device) and the raw pointers belong to the same device.  No-op for the CPU stand-in engine of the tests."""
+
+    def __init__(self, device):
+        self.guard = torch.cuda.device(device) if torch.device(device).type == "cuda" else None
+
+    def __enter__(self):
+        if self.guard is not None:
+            self.guard.__enter__()
+
+    def __exit__(self, *exc):
+        if self.guard is not None:
+            self.guard.__exit__(*exc)
+        return False
 
 
 def _gather_packed(eng, ws, image_features, text_features, rank, world, gather_images=True):
@@ -420,6 +528,7 @@ def _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, wor
 
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
+    @_scoped
     def forward(ctx, image_features, text_features, logit_scale, module):
         eng = _engine()
         _check_inputs(image_features, text_features)
@@ -444,24 +553,27 @@ class _ClipLossFn(torch.autograd.Function):
                           and n * N >= _FWD_DS_MIN_PAIRS and d % 4 == 0 and eng.fwd_row_ent_ok(n, N, n))
         _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, use_emat,
                      gather_images=not use_emat and any(ctx.needs_input_grad), row_ent=ctx.fwd_ds)
-        loss = torch.empty((1,), dtype=torch.float32, device=device)
+        loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
         eng.clip_loss(ws.lse2_row_all[rows], ws.lse2_col_all, ws.diag2, n, rank * n, loss)
-        ctx.loss_local = loss.clone() if (world > 1 and not module.local_loss) else loss
+        ctx.loss_local = loss.clone()    # private: the caller may modify the returned loss in place (loss /= accum)
         if world > 1 and not module.local_loss:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
             loss /= world
 
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+        ctx.lease = module._pool.lease(ws)
         ctx.scale = scale
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         if not any(ctx.needs_input_grad):
-            module._pool.give_back(ws)   # inference / no_grad: nothing will come back for these buffers
-        return loss.reshape(())
+            ctx.lease.release()          # inference / no_grad: nothing will come back for these buffers
+        return loss
 
     @staticmethod
+    @_scoped
     def backward(ctx, grad_output):
         eng = _engine()
+        ctx.lease.check()
         ws, module = ctx.ws, ctx.module
         n, N, d, rank, world = ctx.shape_args
         device = ws.img_all.device
@@ -560,7 +672,7 @@ class _ClipLossFn(torch.autograd.Function):
                     ds /= world
             shp, dt = ctx.scale_meta
             d_scale = ds.reshape(shp).to(dt)
-        module._pool.give_back(ws)
+        ctx.lease.release()
         return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None
 
 
@@ -637,6 +749,7 @@ class _MultiPositiveFn(torch.autograd.Function):
     [n, N] mask and their softmaxes)."""
 
     @staticmethod
+    @_scoped
     def forward(ctx, image_features, text_features, logit_scale, labels, delta, module):
         eng = _engine()
         _check_inputs(image_features, text_features)
@@ -686,20 +799,23 @@ class _MultiPositiveFn(torch.autograd.Function):
         ln2 = 0.6931471805599453
         loss_img = (ws.lse2_row_all[rows] * ln2 - pos_img).mean()
         loss_txt = (ws.lse2_col_all[rows] * ln2 - pos_txt).mean()
-        loss = (delta * loss_img + (1.0 - delta) * loss_txt).reshape(1)
+        loss = torch.empty((), dtype=torch.float32, device=device).copy_(delta * loss_img + (1.0 - delta) * loss_txt)
 
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
-        ctx.scale, ctx.delta, ctx.loss_local = scale, float(delta), loss
+        ctx.lease = module._pool.lease(ws)
+        ctx.scale, ctx.delta, ctx.loss_local = scale, float(delta), loss.clone()
         ctx.corr = (corr_i, corr_t)
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         if not keep_e:
-            module._pool.give_back(ws)
-        return loss.reshape(())
+            ctx.lease.release()          # inference / no_grad: nothing will come back for these buffers
+        return loss
 
     @staticmethod
+    @_scoped
     def backward(ctx, grad_output):
         eng = _engine()
+        ctx.lease.check()
         ws, module = ctx.ws, ctx.module
         n, N, d, rank, world = ctx.shape_args
         device = ws.img_all.device
@@ -742,7 +858,7 @@ class _MultiPositiveFn(torch.autograd.Function):
             ds = (gout / ctx.scale) * (ctx.loss_local + (0.6931471805599453 * coef) * ent)
             shp, dt = ctx.scale_meta
             d_scale = ds.reshape(shp).to(dt)
-        module._pool.give_back(ws)
+        ctx.lease.release()
         return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None, None, None
 
 
@@ -769,6 +885,7 @@ class MultiPositiveClipLoss(ClipLoss):
 
 class _SigLipLossFn(torch.autograd.Function):
     @staticmethod
+    @_scoped
     def forward(ctx, image_features, text_features, logit_scale, logit_bias, module):
         eng = _engine()
         _check_inputs(image_features, text_features)
@@ -784,7 +901,7 @@ class _SigLipLossFn(torch.autograd.Function):
         use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat"
         _gather_packed(eng, ws, image_features, text_features, rank, world,
                        gather_images=not use_emat and any(ctx.needs_input_grad))
-        loss = torch.empty((1,), dtype=torch.float32, device=device)
+        loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
         if use_emat:
             # no normaliser: the forward can store G = sigmoid(z) - delta itself
             eng.siglip_fwd_e(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss, ws.gmat_buffer(eng))
@@ -792,17 +909,20 @@ class _SigLipLossFn(torch.autograd.Function):
         else:
             eng.siglip_fwd(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss)
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+        ctx.lease = module._pool.lease(ws)
         ctx.scale, ctx.bias = scale, bias
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         ctx.bias_meta = (logit_bias.shape, logit_bias.dtype) if torch.is_tensor(logit_bias) else None
         if not any(ctx.needs_input_grad):
-            module._pool.give_back(ws)
-        return loss.reshape(())
+            ctx.lease.release()          # inference / no_grad: nothing will come back for these buffers
+        return loss
 
     @staticmethod
+    @_scoped
     def backward(ctx, grad_output):
         eng = _engine()
+        ctx.lease.check()
         ws, module = ctx.ws, ctx.module
         n, N, d, rank, world = ctx.shape_args
         device = ws.img_all.device
@@ -851,7 +971,7 @@ class _SigLipLossFn(torch.autograd.Function):
         if need_b:
             shp, dt = ctx.bias_meta
             d_bias = db.reshape(shp).to(dt)
-        module._pool.give_back(ws)
+        ctx.lease.release()
         return (d_img if need_i else None), (d_txt if need_t else None), d_scale, d_bias, None
 
 

@@ -128,7 +128,7 @@ class StandInEngine:
         self.calls.append("clip_loss")
         cols = lse2_col[label_offset:label_offset + m_rows].double()
         tot = (lse2_row[:m_rows].double() + cols - 2 * diag2[:m_rows].double()).sum()
-        loss[0] = float(tot / LOG2E / (2 * m_rows))
+        loss.view(-1)[0] = float(tot / LOG2E / (2 * m_rows))
 
     def clip_bwd(self, a_rows, b_all, bt_all, shape, lse2_a, lse2_b, scale, w_own, w_oth, coef, grad_out, ws,
                  d_a, d_scale, accumulate):
@@ -293,7 +293,7 @@ class StandInEngine:
         y = -torch.ones_like(z)
         idx = torch.arange(shape.m_rows)
         y[idx, idx + shape.label_offset] = 1.0
-        loss[0] = float(torch.nn.functional.softplus(-y * z).sum() / shape.m_rows)
+        loss.view(-1)[0] = float(torch.nn.functional.softplus(-y * z).sum() / shape.m_rows)
 
     def siglip_bwd(self, a_rows, b_all, bt_all, shape, scale, bias, coef, grad_out, ws, d_a, d_scale, d_bias,
                    accumulate):

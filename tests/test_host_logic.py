@@ -387,3 +387,68 @@ def test_forward_side_d_scale_matches_reference(name, exact):
         used = ret[r]["calls"]
         assert ("clip_fwd_tiles_eu" in used and "row_ent_split" in used) == local      # global-loss modes keep the entropy path
         assert ("clip_fwd_tiles_e" in used) == (not local)
+
+
+# ---- workspace leases: no leak without backward, no silent second backward, bounded pool --------
+def _feat(n=16, d=8, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1).requires_grad_(True),
+            torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1).requires_grad_(True))
+
+
+def test_workspace_returns_when_graph_is_dropped(standin_engine):
+    mod = ClipLoss()
+    i, t = _feat()
+    s = torch.tensor(10.0, requires_grad=True)
+    for _ in range(6):              # forward only, graph dropped every time: the same set must be reused
+        loss = mod(i, t, s)
+        del loss
+    sets = [w for lst in mod._pool._free.values() for w in lst]
+    assert len(sets) == 1 and not sets[0].in_use
+    loss = mod(i, t, s)             # a live graph holds its set ...
+    assert sets[0].in_use
+    loss.backward()                 # ... and backward returns it
+    assert not sets[0].in_use
+
+
+def test_second_backward_raises(standin_engine):
+    mod = ClipLoss()
+    i, t = _feat()
+    s = torch.tensor(10.0, requires_grad=True)
+    loss = mod(i, t, s)
+    loss.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="second time"):
+        loss.backward()
+
+
+def test_returned_loss_may_be_modified_in_place(standin_engine):
+    i, t = _feat(seed=3)
+    s = torch.tensor(10.0, requires_grad=True)
+    ref = ClipLoss()(i, t, s)
+    ref.backward()
+    want = s.grad.clone()
+    s.grad = None
+    loss = ClipLoss()(i, t, s)
+    with torch.no_grad():
+        loss.mul_(0.0)              # e.g. loss /= accum_freq on the returned tensor
+    loss.backward()
+    torch.testing.assert_close(s.grad, want)
+
+
+def test_pool_evicts_idle_keys(standin_engine, monkeypatch):
+    monkeypatch.setenv("MRCLIP_POOL_KEYS", "3")
+    mod = ClipLoss()
+    s = torch.tensor(10.0)
+    for n in (8, 9, 10, 11, 12, 13):          # ragged batch sizes
+        i, t = _feat(n=n)
+        with torch.no_grad():
+            mod(i, t, s)
+    assert len(mod._pool._free) <= 3
+    assert list(mod._pool._free)[-1][1] == 13
+
+
+def test_cpu_tensors_raise_without_engine_override():
+    mrclip_b200.set_engine(None)
+    i, t = _feat()
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        ClipLoss()(i, t, torch.tensor(10.0))
