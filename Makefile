@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -lineinfo -O3 -std=c++17
 CSRC := mrclip_b200/csrc
-HDRS := $(CSRC)/ptx.cuh $(CSRC)/tile_kernel.cuh $(CSRC)/gemm_kernel.cuh $(CSRC)/gemm2_kernel.cuh $(CSRC)/aux_kernels.cuh include/mrclip.h
+HDRS := $(CSRC)/ptx.cuh $(CSRC)/peer_sync.cuh $(CSRC)/peer_kernels.cuh $(CSRC)/tile_kernel.cuh $(CSRC)/gemm_kernel.cuh $(CSRC)/gemm2_kernel.cuh $(CSRC)/aux_kernels.cuh include/mrclip.h
 
 all: mrclip_b200/libmrclip.so mrclip_b200/selftest
 

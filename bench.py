@@ -25,6 +25,17 @@ DIM = 768
 LOGIT_SCALE = 14.285714
 METRIC = "ClipLoss fwd+bwd pairs/sec"
 UNIT = "pairs/s"
+# BASELINE.json configs[0..3] (the default run is c3, the configuration the metric is quoted on)
+CONFIGS = {
+    "c1": dict(workload="clip", global_batch=256, dim=512, local_loss=False, gather_with_grad=False,
+               name="ClipLoss world_size=1, batch 256, dim 512 (BASELINE.json configs[0], the reference's CPU-runnable case)"),
+    "c2": dict(workload="clip", global_batch=4096, dim=512, local_loss=False, gather_with_grad=True,
+               name="ClipLoss gather_with_grad=True, global batch 4096, dim 512 (BASELINE.json configs[1])"),
+    "c3": dict(workload="clip", global_batch=32768, dim=768, local_loss=True, gather_with_grad=True,
+               name="ClipLoss local_loss=True gather_with_grad=True, global batch 32768, dim 768 (BASELINE.json configs[2])"),
+    "c4": dict(workload="siglip", global_batch=16384, dim=768, local_loss=True, gather_with_grad=True,
+               name="SigLipLoss with logit_bias, global batch 16384, dim 768 (BASELINE.json configs[3])"),
+}
 
 
 def parse():
@@ -33,8 +44,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--global-batch", type=int, default=GLOBAL_BATCH)
-    ap.add_argument("--dim", type=int, default=DIM)
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS),
+                    help="one of BASELINE.json's configs (sets workload, global batch, dim and the ClipLoss mode); "
+                         "default: c3, the headline")
+    ap.add_argument("--global-batch", type=int, default=None)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--no-parity", action="store_true", help="skip the pre-timing check against the fp32 torch reference")
     ap.add_argument("--feature-dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-sample-rows", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -44,10 +59,20 @@ def parse():
     ap.add_argument("--workload", default="clip", choices=["clip", "siglip", "mpos"],
                     help="clip = the headline (BASELINE configs[2]); siglip / mpos: extra measurements of the other two "
                          "losses on the same shapes (not the headline metric)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config or "c3"]
+    if args.config is not None:
+        args.workload = cfg["workload"]
+    args.global_batch = args.global_batch or (cfg["global_batch"] if args.config else GLOBAL_BATCH)
+    args.dim = args.dim or (cfg["dim"] if args.config else DIM)
+    args.local_loss, args.gather_with_grad = cfg["local_loss"], cfg["gather_with_grad"]
+    args.config_name = cfg["name"] if (args.global_batch, args.dim, args.workload) == (cfg["global_batch"], cfg["dim"], cfg["workload"]) else None
+    return args
 
 
 def workload_name(args):
+    if getattr(args, "config_name", None):
+        return args.config_name
     if getattr(args, "workload", "clip") == "siglip":
         return f"SigLipLoss with logit_bias, global batch {args.global_batch}, dim {args.dim} (extra; cf. BASELINE.json configs[3])"
     if getattr(args, "workload", "clip") == "mpos":
@@ -66,29 +91,48 @@ def peaks():
 
 
 # ------------------------------------------------------------------------------------------- reference arm
+def reference_timing(args, steps, warmup):
+    """The reference's own module (oracle/_ref, the unmodified files) on the host cores; the port when the copy is absent."""
+    from oracle import ref_runner
+    kind = "siglip" if args.workload == "siglip" else "clip"
+    if ref_runner.available():
+        scale, bias = (10.0, -10.0) if kind == "siglip" else (LOGIT_SCALE, None)
+        return ref_runner.time_reference(args.global_batch, args.dim, steps, warmup, kind=kind, scale=scale,
+                                         bias=-10.0 if bias is None else bias)
+    from oracle.clip_port import time_clip_sample
+    res = time_clip_sample(args.global_batch, args.dim, min(args.cpu_sample_rows, args.global_batch), steps=steps, warmup=warmup)
+    res["kind"] = "port"
+    return res
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    from oracle.clip_port import time_clip_sample
-    res = time_clip_sample(args.global_batch, args.dim, args.cpu_sample_rows, steps=max(1, min(args.steps, 5)),
-                           warmup=max(1, min(args.warmup, 2)))
+    res = reference_timing(args, max(1, args.steps), max(1, args.warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": res["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": max(1, min(args.steps, 5)), "warmup": max(1, min(args.warmup, 2)),
+        "impl": "reference", "metric": metric_name(args), "value": res["pairs_per_s"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": max(1, args.steps), "warmup": max(1, args.warmup),
         "ms_per_step": res["seconds_per_step"] * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "global_batch": args.global_batch, "dim": args.dim,
                    "feature_dtype": "fp32", "logit_scale": LOGIT_SCALE,
-                   "note": "reference algorithm on host cores (oracle/clip_port.py; "
-                   "the reference is pure PyTorch CPU code and /root/reference is absent on the GPU box)"},
-        "cpu_baseline": {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+                   "note": "the reference's own loss module (oracle/_ref: unmodified copy of src/open_clip/loss.py) through its "
+                           "public API on the host cores; each step is the bounded sample described in cpu_baseline.sample"
+                           if res["kind"] == "reference" else
+                           "reference algorithm on host cores (oracle/clip_port.py; oracle/_ref was not shipped)"},
+        "cpu_baseline": {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                          "sample": res["sample"]},
         "e2e": {"value": res["pairs_per_s"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
     return 0
+
+
+def metric_name(args):
+    return METRIC if args.workload == "clip" else METRIC.replace(
+        "ClipLoss", {"siglip": "SigLipLoss", "mpos": "MultiPositiveClipLoss"}[args.workload])
 
 
 # ------------------------------------------------------------------------------------------- clocks sampler
@@ -151,8 +195,6 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"     # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     eng = default_engine()
 

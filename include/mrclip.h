@@ -212,6 +212,64 @@ int mrclip_siglip_fwd_e(const void* a_rows, const void* b_all, mrclip_shape shap
 int mrclip_siglip_e_scalars(mrclip_shape shape, void* ws, float coef, const float* grad_out, float* d_scale,
                             float* d_bias, int accumulate_scalars, void* stream);
 
+/* ---- whole-step entries ------------------------------------------------------------------------------------------
+ * One call launches every kernel of a loss forward (or backward) on `stream`: what ClipLoss.forward / SigLipLoss.forward
+ * (loss.py:128-139, :365-448) and their autograd graph do, behind one C call per direction.  On several ranks (one
+ * process per GPU) nothing but this library's kernels moves data: the packed text rows, the LSE statistics, the
+ * text-gradient tiles and the scalars travel over NVLink peer memory and are synchronised by device-side flags
+ * (csrc/peer_sync.cuh) -- no NCCL call, no host synchronisation, so the step can also be captured into a CUDA graph.
+ * The text all-gather (loss.py:51-57) overlaps the forward tiles: a rank starts on its own columns and picks up the
+ * other ranks' columns as their rows land; the gradient reduce-scatter (torch/distributed/nn/functional.py:343-347) is
+ * fused into the dT GEMM's epilogue.
+ *
+ * mrclip_peer: plumbing of one workspace.  Every buffer named "_peers" is a device array [ranks] of NVLink-mapped
+ * addresses of the SAME symmetric buffer on every rank (own rank included).  ctl_block: symmetric,
+ * mrclip_peer_block_bytes() bytes, zeroed once; ctl: plain device memory, 64 int32, zeroed once.  ranks <= 1: all
+ * pointers may be NULL. */
+typedef struct mrclip_peer {
+  int ranks, rank;
+  const unsigned long long* ctl_block_peers;
+  void* ctl_block;
+  int* ctl;
+  const unsigned long long* txt_peers;    /* bf16 [N, ld] gathered text buffer (the one used by this step) */
+  const unsigned long long* stats_peers;  /* float [ranks][3][N] */
+  const unsigned long long* recv_peers;   /* [ranks][n][d] receive slots of the fused reduce-scatter (fp32 or bf16) */
+  void* recv;                             /* this rank's receive slots */
+  int recv_bf16;
+} mrclip_peer;
+
+typedef struct mrclip_step {
+  mrclip_shape shape;      /* m_rows = n (rows of this rank), n_cols = N = ranks * n, label_offset = rank * n */
+  int ld;                  /* mrclip_padded_dim(d) */
+  int kind;                /* 0 = ClipLoss, 1 = SigLipLoss */
+  int local_loss;          /* ClipLoss on several ranks: 0 = loss and d logit_scale are averaged over the ranks */
+  void* img_rows;          /* bf16 [n, ld]   packed image rows of this rank (written by the forward) */
+  void* txt_all;           /* bf16 [N, ld]   this rank's gathered text buffer (symmetric when ranks > 1) */
+  void* ws;                /* mrclip_workspace_bytes(n, N, d) */
+  void* emat;              /* mrclip_gmat_bytes(n, N): E / G block (NULL: forward only, nothing kept for a backward) */
+  float* stats;            /* float [ranks][3][N]  (symmetric when ranks > 1) */
+  float* lse2_row_all;     /* float [mrclip_padded_cols(N)] */
+  float* lse2_col_all;     /* float [mrclip_padded_cols(N)] */
+  float* msums;            /* float [64][2][ranks] */
+  float* small;            /* float [mrclip_step_small_floats()], zeroed once */
+  mrclip_peer peer;
+} mrclip_step;
+
+size_t mrclip_peer_block_bytes(void);
+size_t mrclip_step_small_floats(void);
+/* 1 when mrclip_step_backward will take d logit_scale from forward-side row sums (the forward must then be told:
+ * fwd_ds), 0 when it uses the entropy sums of the rescale pass.  Pure function of the shape and mode. */
+int mrclip_step_uses_fwd_ds(const mrclip_step* s);
+/* img / txt: this rank's [n, d] feature rows (MRCLIP_DT_*, leading dims in elements).  scale (and bias, SigLIP, may be
+ * NULL) are device scalars.  need_grad == 0: no E / G block is written.  loss_out: device float [1]. */
+int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, long img_ld, const void* txt, int txt_dtype,
+                        long txt_ld, const float* scale, const float* bias, int need_grad, float* loss_out, void* stream);
+/* coef: 1/(2n) (or 1/(2N) for ClipLoss(local_loss=False, gather_with_grad=False)); 1/n for SigLIP.  grad_out: device
+ * float [1] or NULL.  d_img / d_txt: [n, d] of MRCLIP_DT_*; d_scale / d_bias: device float [1] or NULL. */
+int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* grad_out, float coef, void* d_img,
+                         int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
+                         float* d_bias, void* stream);
+
 /* number of kernels this library has launched on behalf of the calling process (for bench accounting) */
 long mrclip_launch_count(void);
 

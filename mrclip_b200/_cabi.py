@@ -59,6 +59,11 @@ SIGNATURES = {
     "mrclip_sum_slots_dot": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
     "mrclip_gmat_gemm_push_bf16": (_I, [_P, Shape, _P, _I, _F, _P, _P, _P, _P, _I, _I, _P]),
     "mrclip_sum_slots_bf16": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
+    "mrclip_peer_block_bytes": (C.c_size_t, []),
+    "mrclip_step_small_floats": (C.c_size_t, []),
+    "mrclip_step_uses_fwd_ds": (_I, [_P]),
+    "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _P, _P]),
+    "mrclip_step_backward": (_I, [_P, _P, _P, _F, _P, _I, _L, _P, _I, _L, _P, _P, _P]),
     "mrclip_launch_count": (_L, []),
 }
 

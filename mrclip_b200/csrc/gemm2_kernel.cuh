@@ -279,6 +279,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (PUSH) bulk_wait0();   // every pushed row is complete before the kernel (and the cross-rank barrier) ends
   }
   tc_fence_before();
+  if (PUSH && p.sig.ranks > 1) peer_signal_when_grid_done(p.sig, CH_DTEXT, gridDim.x);   // (contains the __syncthreads)
   __syncthreads();
   cluster_sync_all();      // nobody frees TMEM or exits while the peer may still signal / read
   if (warp == 1) {

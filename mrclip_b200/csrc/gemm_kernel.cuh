@@ -14,6 +14,7 @@
 // Replaces the autograd matmul-backward GEMMs of loss.py:117-124.
 #pragma once
 #include "aux_kernels.cuh"
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 #include "tile_kernel.cuh"
 
@@ -46,6 +47,8 @@ struct GemmParams {
   // slot peer_rank, through the NVLink-mapped pointer peer[q]: fp32 [ranks][peer_n][d_valid] on every rank
   const unsigned long long* peer;
   int peer_n, peer_rank;
+  // optional: raise CH_DTEXT on every rank when the last CTA's pushed rows have landed (peer_sync.cuh); sig.ranks == 0: off
+  PeerInfo sig;
 };
 
 // destination row of the direct epilogue: local output, or the owner's receive slot over NVLink

@@ -4,6 +4,7 @@
 #include "aux_kernels.cuh"
 #include "gemm2_kernel.cuh"
 #include "gemm_kernel.cuh"
+#include "peer_kernels.cuh"
 #include "tile_kernel.cuh"
 
 #include <atomic>
@@ -277,9 +278,14 @@ int check_shape(const mrclip_shape& s, int ld) {
   return 0;
 }
 
+struct FwdSig {   // TileParams::sig_* (multi-rank forward whose B rows arrive over NVLink while it runs)
+  const int* ready = nullptr;
+  const int* epoch = nullptr;
+  int src_cols = 0, my_src = 0;
+};
 int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld,
             const float* scale, const float* bias, int col_begin, int col_end, void* ws, void* emat,
-            cudaStream_t st, bool row_ent = false) {
+            cudaStream_t st, bool row_ent = false, const FwdSig* sig = nullptr) {
   if (int e = check_shape(sh, ld)) return e;
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
@@ -320,6 +326,15 @@ int run_fwd(int loss_kind, const void* a_rows, const void* b_all, const mrclip_s
   p.sc_part = reinterpret_cast<float2*>(wsb + w.sc_part) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
   p.sc_part2 = reinterpret_cast<float2*>(wsb + w.sc_part2) + (size_t)p.chunk_base * f.num_rb * kEpiWarps;
   p.row_ent = reinterpret_cast<float*>(wsb + w.row_ent);
+  if (sig != nullptr && sig->ready != nullptr && sig->src_cols > 0) {
+    p.sig_ready = sig->ready;
+    p.sig_epoch = sig->epoch;
+    p.src_cols = sig->src_cols;
+    p.my_src = sig->my_src;
+    // own columns first: rotate by the chunk that holds this rank's first column (whole range only)
+    if (col_begin == 0 && col_end == sh.n_cols)
+      p.chunk_rot = (int)(((long)sig->my_src * sig->src_cols) / (f.tiles_per_chunk * kSBN)) % p.num_chunks;
+  }
   if (emat && row_ent && loss_kind == LOSS_CLIP) return launch_tile<MODE_FWDEU, LOSS_CLIP, 256, kSBN>(ma, mb, me, p, st);
   if (emat) {
     if (loss_kind == LOSS_CLIP) return launch_tile<MODE_FWDE, LOSS_CLIP, 256, kSBN>(ma, mb, me, p, st);
@@ -489,6 +504,7 @@ struct DotArgs {   // optional: dot_out += <d_out, dot_feat> / scale  (d(loss)/d
   // optional: fused reduce-scatter, see GemmParams::peer
   const unsigned long long* peer = nullptr;
   int peer_n = 0, peer_rank = 0;
+  PeerInfo sig = {nullptr, nullptr, nullptr, 0, 0};   // raise CH_DTEXT when the pushed tiles have landed
 };
 int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, const void* feat, int d, int ld,
                   float coef, const float* scale, const float* grad_out, void* ws, void* d_out, int out_dtype,
@@ -518,6 +534,7 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
     p.peer = xf.peer;
     p.peer_n = xf.peer_n;
     p.peer_rank = xf.peer_rank;
+    p.sig = xf.sig;
     p.out = d_out;
     p.out_ld = out_ld;
     p.out_dtype = out_dtype;
@@ -989,6 +1006,265 @@ int mrclip_siglip_e_scalars(mrclip_shape shape, void* ws, float coef, const floa
       reinterpret_cast<const float2*>(reinterpret_cast<uint8_t*>(ws) + w.sc_part2),
       (long)f.num_rb * f.total_chunks * kEpiWarps, coef, coef, grad_out, nullptr, d_scale, d_bias, accumulate_scalars, 0);
   g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"
+
+/* ---- whole-step entries (include/mrclip.h): every kernel of a forward / backward behind one call --------------- */
+namespace {
+constexpr int kSmallDot = 0, kSmallR2Row = 64, kSmallLoss = 65, kSmallAcc = 128;
+constexpr size_t kSmallFloats = 128 + 64 * 64 + 128;
+constexpr int kCtlRowEntDone = 16;
+
+PeerInfo make_peer(const mrclip_step* s) {
+  PeerInfo pi;
+  pi.sig_peers = s->peer.ctl_block_peers;
+  pi.sig_local = reinterpret_cast<int*>(s->peer.ctl_block);
+  pi.ctl = reinterpret_cast<PeerCtl*>(s->peer.ctl);
+  pi.ranks = s->peer.ranks > 1 ? s->peer.ranks : 1;
+  pi.rank = s->peer.ranks > 1 ? s->peer.rank : 0;
+  return pi;
+}
+
+int check_step(const mrclip_step* s) {
+  if (!s) return fail(-1, "step: NULL descriptor");
+  if (int e = check_shape(s->shape, s->ld)) return e;
+  const int ranks = s->peer.ranks > 1 ? s->peer.ranks : 1;
+  if (s->ld != mrclip_padded_dim(s->shape.d)) return fail(-1, "step: ld=%d must be mrclip_padded_dim(d)=%d", s->ld, mrclip_padded_dim(s->shape.d));
+  if ((long)s->shape.m_rows * ranks != s->shape.n_cols) return fail(-1, "step: n_cols=%d must be ranks*m_rows=%d*%d", s->shape.n_cols, ranks, s->shape.m_rows);
+  if (!s->img_rows || !s->txt_all || !s->ws || !s->small) return fail(-1, "step: NULL buffer");
+  if (s->kind == 0 && (!s->stats || !s->lse2_row_all || !s->lse2_col_all || !s->msums)) return fail(-1, "step: NULL statistics buffer");
+  if (ranks > 1) {
+    const mrclip_peer& p = s->peer;
+    if (ranks > kPeerMaxRanks) return fail(-1, "step: at most %d ranks", kPeerMaxRanks);
+    if (p.rank < 0 || p.rank >= ranks || s->shape.label_offset != p.rank * s->shape.m_rows) return fail(-1, "step: bad rank / label_offset");
+    if (!p.ctl_block_peers || !p.ctl_block || !p.ctl || !p.txt_peers || !p.recv_peers || !p.recv || (s->kind == 0 && !p.stats_peers))
+      return fail(-1, "step: NULL peer buffer");
+    if (!gemm_pairs()) return fail(-1, "step: the multi-rank step needs the CTA-pair GEMM (unset MRCLIP_GEMM_CTA)");
+  }
+  return 0;
+}
+
+int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img_dtype, long img_ld, const void* txt,
+              int txt_dtype, long txt_ld, cudaStream_t st) {
+  if (img_dtype < 0 || img_dtype > 2 || txt_dtype < 0 || txt_dtype > 2) return fail(-1, "step: bad feature dtype");
+  if (img_ld < s->shape.d || txt_ld < s->shape.d) return fail(-1, "step: feature leading dimension < d");
+  Pack2Params pp;
+  memset(&pp, 0, sizeof pp);
+  pp.img_src = img;
+  pp.txt_src = txt;
+  pp.img_dtype = img_dtype;
+  pp.txt_dtype = txt_dtype;
+  pp.rows = s->shape.m_rows;
+  pp.d = s->shape.d;
+  pp.ld = s->ld;
+  pp.img_src_ld = img_ld;
+  pp.txt_src_ld = txt_ld;
+  pp.img_dst = reinterpret_cast<__nv_bfloat16*>(s->img_rows);
+  pp.txt_peers = s->peer.txt_peers;
+  pp.txt_local = reinterpret_cast<__nv_bfloat16*>(s->txt_all);
+  pp.row0 = s->shape.label_offset;
+  const int vec_ok = (img_ld % 8 == 0 && txt_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
+                      (reinterpret_cast<uintptr_t>(txt) & 15) == 0) ? 1 : 0;
+  const long total = 2L * pp.rows * (pp.ld / 8);
+  long blocks = (total + 255) / 256;
+  if (blocks > 148L * 8) blocks = 148L * 8;
+  pack2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pass's entropy sums on every shape
+  const char* e = getenv("MRCLIP_DS");
+  return (e && strcmp(e, "entropy") == 0) ? 1 : 0;
+}
+}  // namespace
+
+extern "C" {
+
+size_t mrclip_peer_block_bytes(void) { return kPeerBlockBytes; }
+size_t mrclip_step_small_floats(void) { return kSmallFloats; }
+
+int mrclip_step_uses_fwd_ds(const mrclip_step* s) {
+  if (!s || s->kind != 0 || s->peer.ranks <= 1 || !s->local_loss || ds_env_entropy()) return 0;
+  const int n = s->shape.m_rows, N = s->shape.n_cols;
+  if ((long)n * N < (1L << 22) || s->shape.d % 4 != 0) return 0;   // below: the bf16 noise of G in <dT_r, T_r> is not averaged out
+  return mrclip_fwd_row_ent_ok(n, N, n);
+}
+
+int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, long img_ld, const void* txt, int txt_dtype,
+                        long txt_ld, const float* scale, const float* bias, int need_grad, float* loss_out, void* stream) {
+  if (int e = check_step(s)) return e;
+  if (!img || !txt || !scale || !loss_out) return fail(-1, "step_forward: NULL argument");
+  if (need_grad && !s->emat) return fail(-1, "step_forward: need_grad without an E block");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mrclip_shape& sh = s->shape;
+  const int n = sh.m_rows, N = sh.n_cols;
+  const PeerInfo pi = make_peer(s);
+  const int ranks = pi.ranks, rank = pi.rank;
+  if (int e = step_pack(s, pi, img, img_dtype, img_ld, txt, txt_dtype, txt_ld, st)) return e;
+  FwdSig sig;
+  if (ranks > 1) {
+    sig.ready = pi.sig_local + CH_TEXT * kPeerMaxRanks;
+    sig.epoch = &pi.ctl->epoch[CH_TEXT];
+    sig.src_cols = n;
+    sig.my_src = rank;
+  }
+  const FwdPlan f = fwd_plan(n, N);
+  const WsLayout w = ws_layout(n, N, sh.d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(s->ws);
+  if (s->kind == 1) {   // SigLipLoss: softplus sum (+ G block), no statistics
+    if (int e = run_fwd(LOSS_SIGLIP, s->img_rows, s->txt_all, sh, s->ld, scale, bias, 0, N, s->ws, need_grad ? s->emat : nullptr,
+                        st, false, &sig))
+      return e;
+    scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
+                                             (long)f.num_rb * f.total_chunks * kEpiWarps, 1.f / (float)n, 0.f, nullptr,
+                                             nullptr, loss_out, nullptr, 0, 0);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
+  const bool fwd_ds = need_grad && mrclip_step_uses_fwd_ds(s);
+  if (int e = run_fwd(LOSS_CLIP, s->img_rows, s->txt_all, sh, s->ld, scale, nullptr, 0, N, s->ws, need_grad ? s->emat : nullptr,
+                      st, fwd_ds, &sig))
+    return e;
+  const float2* row_part = reinterpret_cast<const float2*>(wsb + w.row_part);
+  const long plane = (long)rank * 3 * N;
+  reduce_rows_pub_kernel<<<ceil_div(n, 256), 256, 0, st>>>(row_part, f.total_chunks * 2, n, f.m_pad, s->peer.stats_peers,
+                                                          s->stats, plane + 2L * N, pi);
+  g_launches.fetch_add(1);
+  if (fwd_ds) {
+    const int slots_per_rank = 2 * (n / (f.tiles_per_chunk * kSBN));
+    row_ent_pub_kernel<<<ceil_div(n, 256), 256, ranks * sizeof(float), st>>>(
+        row_part, reinterpret_cast<const float*>(wsb + w.row_ent), f.total_chunks * 2, slots_per_rank, ranks, n, f.m_pad,
+        s->stats + plane + 2L * N, s->small + kSmallAcc, s->peer.ctl + kCtlRowEntDone, s->small + kSmallR2Row, pi);
+    g_launches.fetch_add(1);
+  }
+  {
+    const int bands = ceil_div(n, 32);
+    static bool attr_set = false;
+    if (!attr_set && bands * sizeof(float) > 48 * 1024) {
+      CUDA_TRY(cudaFuncSetAttribute(reduce_cols_pub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr_set = true;
+    }
+    if (bands * sizeof(float) > 200 * 1024) return fail(-1, "m_rows=%d too large for the column reduce", n);
+    reduce_cols_pub_kernel<<<ceil_div(N, 64), 1024, bands * sizeof(float), st>>>(
+        reinterpret_cast<const float*>(wsb + w.col_l), reinterpret_cast<const float*>(wsb + w.col_c), bands, N, f.n_pad,
+        s->peer.stats_peers, s->stats, plane, plane + N, pi);
+    g_launches.fetch_add(1);
+  }
+  merge_stats_kernel<<<ceil_div(f.n_pad, 256), 256, 0, st>>>(s->stats, ranks, n, N, f.n_pad, s->lse2_col_all, s->lse2_row_all, pi);
+  const int publish = (ranks > 1 && !s->local_loss) ? 1 : 0;
+  clip_loss_pub_kernel<<<1, 1024, 0, st>>>(s->lse2_row_all + (long)rank * n, s->lse2_col_all,
+                                           reinterpret_cast<const float*>(wsb + w.diag2), n, sh.label_offset,
+                                           s->small + kSmallLoss, loss_out, publish, pi);
+  g_launches.fetch_add(2);
+  if (publish) {
+    scal_mean_kernel<<<1, 64, 0, st>>>(0, CH_LOSS, loss_out, pi);
+    g_launches.fetch_add(1);
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* grad_out, float coef, void* d_img,
+                         int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
+                         float* d_bias, void* stream) {
+  if (int e = check_step(s)) return e;
+  if (!scale || !d_img || !d_txt || !s->emat) return fail(-1, "step_backward: NULL argument");
+  if (d_img_dtype < 0 || d_img_dtype > 2 || d_txt_dtype < 0 || d_txt_dtype > 2) return fail(-1, "step_backward: bad output dtype");
+  cudaStream_t st = (cudaStream_t)stream;
+  const mrclip_shape& sh = s->shape;
+  const int n = sh.m_rows, N = sh.n_cols, d = sh.d, ld = s->ld;
+  const PeerInfo pi = make_peer(s);
+  const int ranks = pi.ranks, rank = pi.rank;
+  const WsLayout w = ws_layout(n, N, d);
+  uint8_t* wsb = reinterpret_cast<uint8_t*>(s->ws);
+  const __nv_bfloat16* txt_rows = reinterpret_cast<const __nv_bfloat16*>(s->txt_all) + (size_t)rank * n * ld;
+  int mode = -1;
+  if (s->kind == 0) {
+    const float* lse_row = s->lse2_row_all + (long)rank * n;
+    mode = ranks > 1 ? (mrclip_step_uses_fwd_ds(s) ? 2 : 3) : (((long)n * N >= (1L << 22)) ? 1 : 0);
+    float* msums = (d_scale && (mode == 0 || mode == 3)) ? s->msums : nullptr;
+    if (int e = mrclip_emat_check(sh, s->ws, lse_row, s->lse2_col_all, stream)) return e;
+    const int* flag = mrclip_emat_flag(sh, s->ws);
+    if (int e = mrclip_clip_gwrite_if(s->img_rows, s->txt_all, sh, ld, lse_row, s->lse2_col_all, scale, 1.f, 1.f, s->ws, s->emat,
+                                      flag, stream))
+      return e;
+    if (int e = mrclip_emat_transform(sh, s->ws, s->emat, lse_row, s->lse2_col_all, reinterpret_cast<const float*>(wsb + w.diag2),
+                                      scale, 1.f, 1.f, flag, msums, 64, n, ranks, stream))
+      return e;
+    if (ranks > 1 && msums) {
+      msums_pub_kernel<<<1, 64, 0, st>>>(msums, 64, s->small + kSmallR2Row, pi);
+      g_launches.fetch_add(1);
+    }
+  } else {
+    if (int e = mrclip_siglip_e_scalars(sh, s->ws, coef, grad_out, d_scale, d_bias, 0, stream)) return e;
+  }
+  if (ranks > 1) {
+    DotArgs xf;
+    xf.peer = s->peer.recv_peers;
+    xf.peer_n = n;
+    xf.peer_rank = rank;
+    xf.sig = pi;
+    if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws,
+                              const_cast<unsigned long long*>(s->peer.recv_peers), s->peer.recv_bf16 ? MRCLIP_DT_BF16 : MRCLIP_DT_F32,
+                              d, xf, st))
+      return e;
+    if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
+                              d_img_ld, DotArgs(), st))
+      return e;
+    const bool dot = (s->kind == 0 && d_scale && mode == 2);
+    const long total = ((d & 3) == 0) ? (long)n * (d / 4) : (long)n * d;
+    long blocks = (total + 255) / 256;
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    if (s->peer.recv_bf16)
+      sum_slots_wait_kernel<true><<<(int)blocks, 256, 0, st>>>(s->peer.recv, ranks, n, d, d_txt, d_txt_dtype, d_txt_ld,
+                                                               dot ? txt_rows : nullptr, ld, s->small + kSmallDot, pi);
+    else
+      sum_slots_wait_kernel<false><<<(int)blocks, 256, 0, st>>>(s->peer.recv, ranks, n, d, d_txt, d_txt_dtype, d_txt_ld,
+                                                                dot ? txt_rows : nullptr, ld, s->small + kSmallDot, pi);
+    g_launches.fetch_add(1);
+  } else {
+    DotArgs xf;
+    if (s->kind == 0 && d_scale && mode == 1) {
+      CUDA_TRY(cudaMemsetAsync(d_scale, 0, sizeof(float), st));
+      xf.dot_feat = s->img_rows;
+      xf.dot_out = d_scale;
+    }
+    if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
+                              d_img_ld, xf, st))
+      return e;
+    if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws, d_txt, d_txt_dtype,
+                              d_txt_ld, DotArgs(), st))
+      return e;
+  }
+  if (s->kind == 0 && d_scale) {
+    DsParams dp;
+    memset(&dp, 0, sizeof dp);
+    dp.mode = mode;
+    dp.gout = grad_out;
+    dp.scale = scale;
+    dp.loss_local = s->small + kSmallLoss;
+    dp.kfac = 0.6931471805599453f * 0.5f / (float)n;
+    dp.msums = s->msums;
+    dp.count = 64 * 2 * ranks;
+    dp.dot_slots = s->small + kSmallDot;
+    dp.r2_row_tot = s->small + kSmallR2Row;
+    dp.ds_out = d_scale;
+    dp.publish = (ranks > 1 && !s->local_loss) ? 1 : 0;
+    if (mode != 1 || dp.publish) {
+      ds_finish_kernel<<<1, 128, 0, st>>>(dp, pi);
+      g_launches.fetch_add(1);
+    }
+    if (dp.publish) {
+      scal_mean_kernel<<<1, 64, 0, st>>>(1, CH_DSCALE, d_scale, pi);
+      g_launches.fetch_add(1);
+    }
+  }
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

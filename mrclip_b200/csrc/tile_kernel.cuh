@@ -24,6 +24,7 @@
 // loop, one elected lane issues), warps 2..9 = epilogue (two warps per TMEM lane quarter, each
 // taking half of the tile's columns, 64 at a time).
 #pragma once
+#include "peer_sync.cuh"
 #include "ptx.cuh"
 #include <cuda_bf16.h>
 #include <math_constants.h>
@@ -85,6 +86,15 @@ struct TileParams {
   const int* run_if;    // optional device flag: the kernel returns at once when *run_if == 0
   int ent;              // GW clip: scalar partials become (sum P_own log2 P_own, sum P_oth log2 P_oth)
   float* row_ent;       // FWDEU: [slots][m_pad]  u of each (row, column-chunk half), relative to row_part's max2
+  // Multi-rank forward over NVLink peer memory (the all-gather of loss.py:51-57 overlapped with the tiles): the B rows of
+  // source rank q were stored into this rank's buffer by q's pack2_push_kernel; a column tile may be loaded once
+  // sig_ready[q] has reached *sig_epoch (peer_sync.cuh, CH_TEXT).  The chunk order is rotated so that the tiles on this
+  // rank's own columns -- which wait for nobody -- run first, then the sources in ring order.
+  const int* sig_ready; // this rank's sig block, CH_TEXT row; null: B is complete at launch
+  const int* sig_epoch; // this rank's epoch of CH_TEXT
+  int src_cols;         // columns per source rank
+  int my_src;           // this rank
+  int chunk_rot;        // item order: chunk (c + chunk_rot) % num_chunks is the c-th to run
 };
 
 template <int LEN, int OFF>
@@ -211,7 +221,8 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     } else {
       dc = 0;
     }
-    chunk = rest;
+    chunk = rest + p.chunk_rot;
+    if (chunk >= p.num_chunks) chunk -= p.num_chunks;
     t0 = p.tile_begin + chunk * p.tiles_per_chunk;
     t1 = min(t0 + p.tiles_per_chunk, p.tile_end);
   };
@@ -227,10 +238,22 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           phase ^= 1;
         }
       };
+      unsigned long long src_ready = 0ull;     // sources whose rows are known to have landed
+      const int want_epoch = p.sig_ready != nullptr ? ld_relaxed_gpu(p.sig_epoch) : 0;
       for (int item = blockIdx.x; item < p.num_items; item += gridDim.x) {
         int rb, dc, chunk, t0, t1;
         decode(item, rb, dc, chunk, t0, t1);
         auto load_s = [&](int t) {
+          if (p.sig_ready != nullptr) {
+            const int q0 = (t * BN) / p.src_cols, q1 = min((t + 1) * BN - 1, p.n_cols - 1) / p.src_cols;
+            for (int q = q0; q <= q1; ++q) {
+              if (q == p.my_src || ((src_ready >> q) & 1ull)) continue;
+              if (lane == 0) peer_wait_one(p.sig_ready, 0, q, want_epoch);
+              __syncwarp();
+              fence_proxy_async_all();     // the acquire (generic proxy) before the TMA reads (async proxy) of those rows
+              src_ready |= 1ull << q;
+            }
+          }
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(bar_empty(stage), phase ^ 1);
             if (elect_one()) {

@@ -182,6 +182,15 @@ class _Workspace:
         self.msums = torch.zeros((64, 2, world), dtype=f32, device=device)   # 64 slots against atomic contention
         self.dot_slots = torch.zeros((64,), dtype=f32, device=device)        # <dT_r, T_r> partials (MRCLIP_DS=fwd)
         self.has_emat = False
+        self.plans = {}
+
+    def step_plan(self, eng, kind, local_loss, rank):
+        """Descriptors of the whole-step C entries for this workspace (mrclip_b200/step.py), made on first use."""
+        key = (kind, bool(local_loss), rank)
+        if key not in self.plans:
+            from .step import StepPlan
+            self.plans[key] = StepPlan(eng, self, kind, local_loss, rank)
+        return self.plans[key]
 
     def gmat_buffer(self, eng):
         """bf16 scratch for the materialised gradient block G (n x N), allocated on first use."""
@@ -197,9 +206,9 @@ class _Workspace:
         if self.push is None:
             self.push = False
             if self.img_all.is_cuda and os.environ.get("MRCLIP_RS", "push").lower() != "nccl":
-                # MRCLIP_PUSH_DTYPE=bf16: half the NVLink bytes
+                # bf16 payload (default; MRCLIP_PUSH_DTYPE=fp32 for the wide one): half the NVLink bytes
                 pdt = torch.float32
-                if os.environ.get("MRCLIP_PUSH_DTYPE", "fp32").lower() == "bf16" and self.d % 8 == 0:
+                if os.environ.get("MRCLIP_PUSH_DTYPE", "bf16").lower() == "bf16" and self.d % 8 == 0:
                     pdt = torch.bfloat16
                 bufs = _symmetric_alloc([((self.world, self.n, self.d), pdt)], self.img_all.device, self.world,
                                         "the gradient reduce-scatter")
@@ -262,8 +271,10 @@ def _symmetric_alloc(specs, device, world, what):
 def _symmetric_buffers(ws, device):
     """Collective: two text buffers (alternated per step) and the statistics block.  None when unavailable."""
     bufs = _symmetric_alloc([((ws.N, ws.ld), torch.bfloat16), ((ws.N, ws.ld), torch.bfloat16),
-                             ((ws.world, 3, ws.N), torch.float32)], device, ws.world, "the all-gathers")
-    return None if bufs is None else {"txt": bufs[:2], "stats": bufs[2]}
+                             ((ws.world, 3, ws.N), torch.float32), ((1024,), torch.int32)], device, ws.world,
+                            "the all-gathers")
+    # "ctl": the flag / scalar block of csrc/peer_sync.cuh (mrclip_peer_block_bytes() = 4096 bytes, zeroed)
+    return None if bufs is None else {"txt": bufs[:2], "stats": bufs[2], "ctl": bufs[3]}
 
 
 def _backend(eng, ws):
@@ -343,6 +354,29 @@ class _WorkspacePool:
     def lease(w):
         return _Lease(w)
 
+
+
+def _step_path_ok(eng, ws, world, need_grad):
+    """The whole-step C entries (csrc/mrclip_cabi.cu, mrclip_step_*) serve the emat pipeline on one rank and, on several,
+    over NVLink peer memory.  MRCLIP_STEP=py keeps the per-kernel Python orchestration (also what the CPU tests with a
+    stand-in engine and the NCCL fallbacks use)."""
+    if _engine_override is not None or os.environ.get("MRCLIP_STEP", "c").lower() == "py":
+        return False
+    if need_grad and _backend(eng, ws) != "emat":
+        return False
+    if world > 1:
+        if ws.sym is None or ws.n < 8 or world > 64 or ws.N % 4 != 0:
+            return False
+        if os.environ.get("MRCLIP_RS", "push").lower() == "nccl" or os.environ.get("MRCLIP_GEMM_CTA") == "1":
+            return False
+        if need_grad and ws.push_buffers(0) is None:
+            return False
+    return True
+
+
+def _rows_major(x):
+    x = x.detach()
+    return x if x.stride(1) == 1 else x.contiguous()
 
 
 def _scalar_f32(x, device):
@@ -545,11 +579,32 @@ class _ClipLossFn(torch.autograd.Function):
         split_g = world > 1 and module.local_loss and not module.gather_with_grad
         split_g = split_g or (world > 1 and (n < 8 or world > 64))   # limits of the per-owner entropy sums
         use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat" and not split_g
-        # MRCLIP_DS=fwd (opt-in, not validated on hardware yet): d logit_scale of the multi-rank local loss from
-        # forward-side row sums and <dT_r, T_r>, so that the rescale pass carries no entropy arithmetic
+        # d logit_scale of the multi-rank local loss from forward-side row sums and <dT_r, T_r>, so that the rescale pass
+        # carries no entropy arithmetic (MRCLIP_DS=entropy switches back to the entropy sums)
+        need_grad = any(ctx.needs_input_grad)
+        ctx.fast = None
+        if (not split_g or not need_grad) and _step_path_ok(eng, ws, world, need_grad):
+            # one C call launches the whole forward (csrc/mrclip_cabi.cu: mrclip_step_forward); on several ranks the text
+            # all-gather rides on NVLink peer stores and overlaps the tiles on this rank's own columns
+            plan = ws.step_plan(eng, 0, module.local_loss or world == 1, rank)
+            if world > 1:
+                ws.flip ^= 1
+            loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
+            plan.forward(eng, ws.flip if world > 1 else 0, _rows_major(image_features), _rows_major(text_features), scale,
+                         None, need_grad, loss)
+            ws.has_emat = need_grad
+            ctx.fast = (plan, ws.flip if world > 1 else 0)
+            ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
+            ctx.lease = module._pool.lease(ws)
+            ctx.scale = scale
+            ctx.in_dtypes = (image_features.dtype, text_features.dtype)
+            ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
+            if not need_grad:
+                ctx.lease.release()
+            return loss
         ctx.fwd_ds = bool(use_emat and world > 1 and module.local_loss and module.gather_with_grad
                           and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
-                          and os.environ.get("MRCLIP_DS", "entropy").lower() == "fwd"
+                          and os.environ.get("MRCLIP_DS", "fwd").lower() != "entropy"
                           and n * N >= _FWD_DS_MIN_PAIRS and d % 4 == 0 and eng.fwd_row_ent_ok(n, N, n))
         _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, world, use_emat,
                      gather_images=not use_emat and any(ctx.needs_input_grad), row_ent=ctx.fwd_ds)
@@ -593,7 +648,12 @@ class _ClipLossFn(torch.autograd.Function):
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
         ds_done = False
-        if ws.has_emat:
+        if ctx.fast is not None:
+            plan, flip = ctx.fast
+            ds = torch.empty((1,), dtype=torch.float32, device=device) if need_s else None
+            plan.backward(flip, ctx.scale, gout, coef, d_img, d_txt, ds, None)
+            ds_done = True
+        elif ws.has_emat:
             gmat = ws.gmat_buffer(eng)
             # d logit_scale: one rank with a large block takes <dI, I>/scale from the GEMM's reduce (free; the bf16
             # rounding of G averages out); otherwise the rescale pass accumulates the softmax entropies, which is
@@ -899,10 +959,22 @@ class _SigLipLossFn(torch.autograd.Function):
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
         use_emat = any(ctx.needs_input_grad) and _backend(eng, ws) == "emat"
-        _gather_packed(eng, ws, image_features, text_features, rank, world,
-                       gather_images=not use_emat and any(ctx.needs_input_grad))
         loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
-        if use_emat:
+        ctx.fast = None
+        if _step_path_ok(eng, ws, world, any(ctx.needs_input_grad)):
+            plan = ws.step_plan(eng, 1, True, rank)
+            if world > 1:
+                ws.flip ^= 1
+            plan.forward(eng, ws.flip if world > 1 else 0, _rows_major(image_features), _rows_major(text_features), scale,
+                         bias, any(ctx.needs_input_grad), loss)
+            ws.has_emat = any(ctx.needs_input_grad)
+            ctx.fast = (plan, ws.flip if world > 1 else 0)
+        else:
+            _gather_packed(eng, ws, image_features, text_features, rank, world,
+                           gather_images=not use_emat and any(ctx.needs_input_grad))
+        if ctx.fast is not None:
+            pass
+        elif use_emat:
             # no normaliser: the forward can store G = sigmoid(z) - delta itself
             eng.siglip_fwd_e(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss, ws.gmat_buffer(eng))
             ws.has_emat = True
@@ -938,7 +1010,10 @@ class _SigLipLossFn(torch.autograd.Function):
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
         # every rank's loss touches T_r: the column block gives the summed (W x) text gradient directly
-        if ws.has_emat:
+        if ctx.fast is not None:
+            plan, flip = ctx.fast
+            plan.backward(flip, ctx.scale, gout, coef, d_img, d_txt, ds, db)
+        elif ws.has_emat:
             gmat = ws.gmat_buffer(eng)
             eng.siglip_e_scalars(shape, ws.scratch, coef, gout, ds, db, False)
             if world == 1:

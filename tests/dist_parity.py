@@ -19,7 +19,6 @@ one line per case / backend with the worst error over ranks.
 """
 import os
 import sys
-import time
 
 import torch
 import torch.distributed as dist
@@ -34,17 +33,18 @@ from mrclip_b200 import ClipLoss, MultiPositiveClipLoss, SigLipLoss  # noqa: E40
 CASES = {
     "c3": dict(kind="clip", N=32768, D=768, scale=14.285714, modes=[(True, True)]),
     "c2": dict(kind="clip", N=4096, D=512, scale=14.285714, modes=[(False, True), (True, True), (True, False), (False, False)]),
-    "c2s100": dict(kind="clip", N=4096, D=512, scale=100.0, modes=[(True, True)], grad_output=65536.0),
+    # (weakly correlated pairs: at scale 100 the usual 0.5 mix saturates the loss to ~1e-30 and every gradient to 0)
+    "c2s100": dict(kind="clip", N=4096, D=512, scale=100.0, modes=[(True, True)], grad_output=65536.0, corr=0.06),
     "c4": dict(kind="siglip", N=16384, D=768, scale=10.0, bias=-10.0),
     "mpos": dict(kind="mpos", N=8192, D=512, scale=14.285714, classes=512, delta=0.3),
-    "ragged": dict(kind="clip", n=1000, D=200, scale=30.0, modes=[(True, True), (False, True)]),
+    "ragged": dict(kind="clip", n=1000, D=200, scale=30.0, modes=[(True, True), (False, True)], corr=0.2),
 }
 
 
-def features(N, D, seed, device):
+def features(N, D, seed, device, corr=0.5):
     g = torch.Generator().manual_seed(seed)
     img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
-    txt = torch.nn.functional.normalize(0.5 * img + 0.5 * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
+    txt = torch.nn.functional.normalize(corr * img + (1.0 - corr) * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
     return img.bfloat16().to(device), txt.bfloat16().to(device)
 
 
@@ -67,7 +67,7 @@ def main():
         if N % world:
             continue
         n, D = N // world, c["D"]
-        img, txt = features(N, D, 1234 + len(name) + N, dev)
+        img, txt = features(N, D, 1234 + len(name) + N, dev, c.get("corr", 0.5))
         rows = slice(rank * n, (rank + 1) * n)
         go = float(c.get("grad_output", 1.0))
         modes = c.get("modes", [(True, True)])
@@ -78,8 +78,6 @@ def main():
                 i = img[rows].clone().requires_grad_(True)
                 t = txt[rows].clone().requires_grad_(True)
                 s = torch.tensor(c["scale"], device=dev, requires_grad=True)
-                ours = {}
-                t0 = time.perf_counter()
                 if c["kind"] == "clip":
                     ll, gg = mode
                     mod = ClipLoss(local_loss=ll, gather_with_grad=gg, cache_labels=True, rank=rank, world_size=world)

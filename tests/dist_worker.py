@@ -31,13 +31,14 @@ def main():
         m = case["meta"]
         assert case["world"] == world, (name, case["world"], world)
         # emat: collectives over NVLink peer memory (push all-gathers, GEMM push epilogue); emat-nccl: the same through NCCL
-        backends = ("emat", "emat-nccl", "gmat", "fused")
-        if os.environ.get("MRCLIP_TEST_PUSHBF16") == "1":     # opt-in: bf16 payload of the fused GEMM -> reduce-scatter
-            backends += ("emat-bf16",)
+        # emat: whole-step C entries, every exchange over NVLink peer memory (bf16 gradient tiles); emat-f32: the same with
+        # the fp32 payload; emat-py: the per-kernel Python orchestration over peer memory; emat-nccl: over NCCL
+        backends = ("emat", "emat-f32", "emat-py", "emat-nccl", "gmat", "fused")
         for backend in backends:
             os.environ["MRCLIP_BWD"] = backend.split("-")[0]
             os.environ["MRCLIP_RS"] = "nccl" if backend.endswith("-nccl") else "push"
-            os.environ["MRCLIP_PUSH_DTYPE"] = "bf16" if backend.endswith("-bf16") else "fp32"
+            os.environ["MRCLIP_PUSH_DTYPE"] = "fp32" if backend.endswith("-f32") else "bf16"
+            os.environ["MRCLIP_STEP"] = "py" if backend.endswith("-py") else "c"
             os.environ["MRCLIP_AG"] = os.environ["MRCLIP_RS"]      # all-gathers: NCCL or peer stores, likewise
             n = case["image"].shape[0] // world
             rows = slice(rank * n, (rank + 1) * n)
@@ -46,7 +47,7 @@ def main():
             s = torch.tensor(float(m["scale"]), device=dev, requires_grad=True)
             ref = case["ranks"][rank]
             if m["kind"] == "mpos":
-                if backend not in ("emat", "emat-nccl", "emat-bf16"):
+                if not backend.startswith("emat"):
                     continue        # the multi-positive loss always runs the E-block pipeline
                 mod = MultiPositiveClipLoss(local_loss=bool(m["local_loss"]), gather_with_grad=bool(m["gather_with_grad"]),
                                             rank=rank, world_size=world)
@@ -75,10 +76,11 @@ def main():
                 failures.append((name, backend, rank, bad, errs))
             if rank == 0:
                 print(f"{name:32s} {backend:9s} " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
-    if os.environ.get("MRCLIP_TEST_FWDDS") == "1":
-        # opt-in (not validated on hardware yet): MRCLIP_DS=fwd against the entropy path on the same inputs, at a size
-        # where <dT_r, T_r> averages the bf16 rounding of G out (n*N >= 2^22)
+    for step in ("c", "py"):
+        # forward-side d logit_scale against the entropy path on the same inputs, at a size where <dT_r, T_r> averages
+        # the bf16 rounding of G out (n*N >= 2^22); whole-step C entries and Python orchestration
         os.environ["MRCLIP_BWD"], os.environ["MRCLIP_RS"], os.environ["MRCLIP_AG"] = "emat", "push", "push"
+        os.environ["MRCLIP_STEP"] = step
         N, D = 16384, 384
         n = N // world
         g = torch.Generator().manual_seed(77)
@@ -93,12 +95,13 @@ def main():
             mod = ClipLoss(local_loss=True, gather_with_grad=True, rank=rank, world_size=world)
             (mod(i, t, s) * 3.0).backward()
             res[mode] = (s.grad.item(), i.grad.float().cpu().numpy(), t.grad.float().cpu().numpy())
-        os.environ["MRCLIP_DS"] = "entropy"
+        os.environ["MRCLIP_DS"] = "fwd"
         errs = dict(d_scale=abs(res["fwd"][0] - res["entropy"][0]) / abs(res["entropy"][0]),
                     d_image=rel_err(res["fwd"][1], res["entropy"][1]), d_text=rel_err(res["fwd"][2], res["entropy"][2]))
-        print(f"rank {rank} MRCLIP_DS=fwd vs entropy: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
+        print(f"rank {rank} MRCLIP_STEP={step} MRCLIP_DS=fwd vs entropy: " + " ".join(f"{k}={v:.2e}" for k, v in errs.items()), flush=True)
         if errs["d_scale"] > 2e-3 or errs["d_image"] > 1e-6 or errs["d_text"] > 1e-6:
             failures.append(("fwd_ds", "emat", rank, list(errs), errs))
+    os.environ["MRCLIP_STEP"] = "c"
     flag = torch.tensor([len(failures)], device=dev)
     dist.all_reduce(flag)
     for f in failures:

@@ -57,5 +57,5 @@ def test_product_refuses_to_run_without_gpu():
     mrclip_b200.set_engine(None)
     loss = mrclip_b200.ClipLoss()
     x = torch.nn.functional.normalize(torch.randn(8, 16), dim=-1)
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
+    with pytest.raises(RuntimeError, match="no CPU (fallback|path)"):
         loss(x.requires_grad_(True), x.clone(), torch.tensor(10.0))

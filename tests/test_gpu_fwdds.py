@@ -1,16 +1,12 @@
-"""Opt-in GPU checks (``MRCLIP_TEST_FWDDS=1 pytest -m gpu tests/test_gpu_fwdds.py``) of the kernels behind MRCLIP_DS=fwd
-(tile_kernel<MODE_FWDEU>, row_ent_split_kernel, sum_slots_dot_kernel) against fp32/fp64 torch on the same inputs.
-Skipped by default: that path has not run on hardware yet; the multi-rank comparison against the
-entropy path is in tests/dist_worker.py under the same switch."""
-import os
-
+"""The kernels behind the forward-side d logit_scale (tile_kernel<MODE_FWDEU>, row_ent_split_kernel,
+sum_slots_dot_kernel) against fp32/fp64 torch on the same inputs; the multi-rank comparison against the entropy path is
+in tests/dist_worker.py."""
 import pytest
 import torch
 
 from conftest import has_b200
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MRCLIP_TEST_FWDDS") != "1", reason="opt-in: set MRCLIP_TEST_FWDDS=1")]
+pytestmark = pytest.mark.gpu
 
 LOG2E = 1.4426950408889634
 
