@@ -221,7 +221,8 @@ def run_ours(args):
         lab_all = torch.randint(0, max(N // 16, 1), (N,), generator=torch.Generator().manual_seed(99))
         labels_d = lab_all[rows].to(dev)
     else:
-        loss_mod = ClipLoss(local_loss=True, gather_with_grad=True, cache_labels=True, rank=rank, world_size=world)
+        loss_mod = ClipLoss(local_loss=args.local_loss, gather_with_grad=args.gather_with_grad, cache_labels=True,
+                            rank=rank, world_size=world)
 
     def step(i, t):
         i.grad = t.grad = scale.grad = None
@@ -260,6 +261,39 @@ def run_ours(args):
 
     for _ in range(max(args.warmup, 3)):
         step(img_d, txt_d)
+
+    # parity before timing: this very step (same tensors, same collectives) against the reference's fp32 torch graph
+    # evaluated on the GPU (tests/torch_ref.py, pinned to the reference-generated goldens by tests/test_torch_ref.py)
+    parity = None
+    if not args.no_parity:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import torch_ref
+        torch.backends.cuda.matmul.allow_tf32 = False
+        loss_t = step(img_d, txt_d)
+        ours = dict(loss=loss_t.detach(), d_image=img_d.grad, d_text=txt_d.grad, d_scale=scale.grad)
+        if args.workload == "siglip":
+            ours["d_bias"] = bias.grad
+            ref = torch_ref.siglip_reference(img_d, txt_d, float(scale), float(bias), rank, world)
+        elif args.workload == "mpos":
+            ref = torch_ref.mpos_reference(img_d, txt_d, float(scale), labels_d, 0.5, rank, world)
+        else:
+            ref = torch_ref.clip_reference(img_d, txt_d, float(scale), args.local_loss, args.gather_with_grad, rank, world)
+        errs, bad = torch_ref.compare(ours, ref)
+        worst = torch.tensor([errs.get(k, 0.0) for k in ("loss", "d_image", "d_text", "d_scale", "d_bias")] + [float(len(bad))],
+                             device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        parity = {"reference": "fp32 torch restatement of the reference's per-rank graph (tests/torch_ref.py), same inputs",
+                  "worst_over_ranks": {k: float(v) for k, v in zip(("loss", "d_image", "d_text", "d_scale", "d_bias"), worst[:5].tolist())},
+                  "tolerance": {"loss": 1e-3, "gradients": 1e-2}, "ok": bool(worst[5].item() == 0)}
+        del ref, ours
+        torch.cuda.empty_cache()
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"error": "parity check failed before timing", "parity": parity}), flush=True)
+            return 1
+        for _ in range(3):
+            step(img_d, txt_d)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -307,7 +341,12 @@ def run_ours(args):
                "gmat_gemm": "gemm2_kernel (dA = G.B / dB = G^T.A from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
                "gmat_gemm_dot": "gemm2_kernel (dA = G.B from the bf16 gradient block, CTA pairs, 2nND flop per launch)",
                "gmat_gemm_push": "gemm2_kernel<PUSH> (dB partial = G^T.A, tiles pushed to their owner over NVLink, 2nND flop)",
-               "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)"}
+               "clip_bwd": "tile_kernel<MODE_BWD> (fused S recompute + dA contraction, 2nND algorithmic flop)",
+               # launch groups of the whole-step C entries (mrclip_prof_report)
+               "fwd_tiles": "tile_kernel<MODE_FWDE/FWDEU> (S = A.B^T tiles + online LSE + bf16 E block out, 2nND flop)",
+               "gemm_dI": "gemm2_kernel (dI = G.T from the bf16 gradient block, CTA pairs, + split-K reduce; 2nND flop)",
+               "gemm_dT": "gemm2_kernel<A_MN> (dT = G^T.I from the bf16 gradient block, CTA pairs; 2nND flop)",
+               "gemm_dT_push": "gemm2_kernel<A_MN, PUSH> (dT partial = G^T.I, tiles pushed to their owner over NVLink; 2nND flop)"}
     TIMED = ["pack", "transpose", "clip_fwd_tiles", "clip_fwd_tiles_e", "siglip_fwd_e", "clip_fwd_reduce", "lse2_merge",
              "clip_loss", "emat_to_gmat", "clip_gwrite", "gmat_gemm", "gmat_gemm_dot", "gmat_gemm_push", "push_copy",
              "sum_slots", "clip_bwd", "clip_fwd_tiles_eu", "row_ent_split", "sum_slots_dot", "sum_slots_bf16"]
@@ -342,16 +381,34 @@ def run_ours(args):
                 return r
             return inner
         setattr(dist, k, make(k, comm_orig[k]))
-    prof_steps = min(args.steps, 10)
+    # same number of steps as the timed loop, started from the same state (short idle first), so that the per-op numbers
+    # see the clocks the timed loop saw; the pass itself is timed so that the two can be compared
+    import ctypes
+    prof_steps = args.steps
+    torch.cuda.synchronize()
+    time.sleep(0.5)
+    eng.lib.mrclip_prof_enable(1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
     for _ in range(prof_steps):
         step(img_d, txt_d)
+    p1.record()
     torch.cuda.synchronize()
+    op_pass_ms = p0.elapsed_time(p1) / prof_steps
     for k in TIMED:
         setattr(eng, k, originals[k])
     for k in COMM:
         setattr(dist, k, comm_orig[k])
     per_op_ms = {k: sum(a.elapsed_time(b) for a, b in v) / prof_steps for k, v in ev.items() if v}
     per_op_calls = {k: len(v) // prof_steps for k, v in ev.items() if v}
+    buf = ctypes.create_string_buffer(1 << 14)
+    if eng.lib.mrclip_prof_report(buf, len(buf)) == 0:
+        for item in buf.value.decode().split(";"):
+            if item:
+                name, ms, cnt = item.split(":")
+                per_op_ms[name] = float(ms) / prof_steps
+                per_op_calls[name] = max(int(cnt) // prof_steps, 1)
+    eng.lib.mrclip_prof_enable(0)
     dom = max((k for k in per_op_ms if k in ALG_OPS), key=lambda k: per_op_ms[k])
     kern_ms = per_op_ms[dom] / per_op_calls[dom]
     alg_flops_per_launch = 2.0 * n * N * D       # one of the three algorithmic N x N x D contractions
@@ -397,19 +454,20 @@ def run_ours(args):
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        from oracle.clip_port import time_clip_sample
-        res = time_clip_sample(N, D, args.cpu_sample_rows, steps=3, warmup=1)
-        cpu_base = {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": "port",
+        res = reference_timing(args, steps=5, warmup=2)
+        cpu_base = {"value": res["pairs_per_s"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
                     "sample": res["sample"]}
 
     if rank == 0:
+        # DRAM bytes of the dominant kernel from an ncu --set full capture of THIS shape (profiles/traffic.json, keyed
+        # "<launch group>@n<rows>xN<cols>xD<dim>"); null when no capture of the shape exists
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tp):
-            traffic = json.load(open(tp)).get(dom)
+            traffic = json.load(open(tp)).get(f"{dom}@n{n}xN{N}xD{D}")
         ws_mb = eng.workspace_bytes(n, N, D) / 2 ** 20
         line = {
-            "metric": METRIC if args.workload == "clip" else METRIC.replace("ClipLoss", {"siglip": "SigLipLoss", "mpos": "MultiPositiveClipLoss"}[args.workload]), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload_name(args), "global_batch": N, "dim": D, "rows_per_gpu": n,
@@ -429,11 +487,14 @@ def run_ours(args):
             "gpu_launches": launches,
             "host_issue_ms_per_step": host_issue_ms,    # close to ms_per_step => the step is host-bound
             "op_ms_per_step": {k: round(v, 4) for k, v in per_op_ms.items()},
+            "op_pass_ms_per_step": round(op_pass_ms, 4),     # the per-op pass as a whole (events enabled), cf. ms_per_step
             "backward_backend": os.environ.get("MRCLIP_BWD", "auto"),
-            "knobs": {k: os.environ[k] for k in ("MRCLIP_DS", "MRCLIP_PUSH_DTYPE", "MRCLIP_AG", "MRCLIP_RS", "MRCLIP_GEMM_CTA")
+            "knobs": {k: os.environ[k] for k in ("MRCLIP_STEP", "MRCLIP_DS", "MRCLIP_PUSH_DTYPE", "MRCLIP_AG", "MRCLIP_RS", "MRCLIP_GEMM_CTA")
                       if k in os.environ},
             "clocks": clocks,
         }
+        if parity is not None:
+            line["parity"] = parity
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if graph_info is not None:

@@ -270,6 +270,12 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
                          int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
                          float* d_bias, void* stream);
 
+/* Optional timing of the launch groups inside the whole-step entries (bench.py's roofline): while enabled, CUDA events
+ * are recorded on the launching stream around each group; mrclip_prof_report synchronises them and writes
+ * "name:total_ms:count;..." into buf.  mrclip_prof_enable(0/1) also discards what was recorded.  Off by default. */
+int mrclip_prof_enable(int on);
+int mrclip_prof_report(char* buf, size_t cap);
+
 /* number of kernels this library has launched on behalf of the calling process (for bench accounting) */
 long mrclip_launch_count(void);
 

@@ -12,7 +12,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -20,6 +23,33 @@ using namespace mrclip;
 
 thread_local std::string g_err;
 std::atomic<long> g_launches{0};
+
+// Optional per-launch-group timing for bench.py (mrclip_prof_enable): CUDA events on the launching stream around each
+// group of the whole-step entries, read back by mrclip_prof_report.  Off by default: no events, no overhead.
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+std::atomic<bool> g_prof_on{false};
+struct ProfScope {
+  cudaStream_t st;
+  cudaEvent_t b = nullptr;
+  ProfScope(const char* name, cudaStream_t s) : st(s) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    b = r.b;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (b) cudaEventRecord(b, st);
+  }
+};
 
 int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -1085,6 +1115,41 @@ int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pa
 
 extern "C" {
 
+int mrclip_prof_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on.store(on != 0);
+  return 0;
+}
+
+int mrclip_prof_report(char* buf, size_t cap) {
+  if (!buf || cap == 0) return fail(-1, "prof_report: no buffer");
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  std::map<std::string, std::pair<double, long>> acc;
+  std::vector<std::string> order;
+  for (auto& r : g_prof) {
+    if (cudaEventSynchronize(r.b) != cudaSuccess) return fail(-1, "prof_report: event not complete");
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) return fail(-1, "prof_report: elapsed time unavailable");
+    if (!acc.count(r.name)) order.push_back(r.name);
+    acc[r.name].first += ms;
+    acc[r.name].second += 1;
+  }
+  std::string out;
+  for (auto& k : order) {
+    char line[160];
+    snprintf(line, sizeof line, "%s:%.6f:%ld;", k.c_str(), acc[k].first, acc[k].second);
+    out += line;
+  }
+  if (out.size() + 1 > cap) return fail(-1, "prof_report: buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return 0;
+}
+
 size_t mrclip_peer_block_bytes(void) { return kPeerBlockBytes; }
 size_t mrclip_step_small_floats(void) { return kSmallFloats; }
 
@@ -1105,7 +1170,10 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
   const int n = sh.m_rows, N = sh.n_cols;
   const PeerInfo pi = make_peer(s);
   const int ranks = pi.ranks, rank = pi.rank;
-  if (int e = step_pack(s, pi, img, img_dtype, img_ld, txt, txt_dtype, txt_ld, st)) return e;
+  {
+    ProfScope ps("pack_push", st);
+    if (int e = step_pack(s, pi, img, img_dtype, img_ld, txt, txt_dtype, txt_ld, st)) return e;
+  }
   FwdSig sig;
   if (ranks > 1) {
     sig.ready = pi.sig_local + CH_TEXT * kPeerMaxRanks;
@@ -1117,9 +1185,13 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
   const WsLayout w = ws_layout(n, N, sh.d);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(s->ws);
   if (s->kind == 1) {   // SigLipLoss: softplus sum (+ G block), no statistics
-    if (int e = run_fwd(LOSS_SIGLIP, s->img_rows, s->txt_all, sh, s->ld, scale, bias, 0, N, s->ws, need_grad ? s->emat : nullptr,
-                        st, false, &sig))
-      return e;
+    {
+      ProfScope ps("fwd_tiles", st);
+      if (int e = run_fwd(LOSS_SIGLIP, s->img_rows, s->txt_all, sh, s->ld, scale, bias, 0, N, s->ws,
+                          need_grad ? s->emat : nullptr, st, false, &sig))
+        return e;
+    }
+    ProfScope ps("fwd_reduce", st);
     scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
                                              (long)f.num_rb * f.total_chunks * kEpiWarps, 1.f / (float)n, 0.f, nullptr,
                                              nullptr, loss_out, nullptr, 0, 0);
@@ -1128,9 +1200,13 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
     return 0;
   }
   const bool fwd_ds = need_grad && mrclip_step_uses_fwd_ds(s);
-  if (int e = run_fwd(LOSS_CLIP, s->img_rows, s->txt_all, sh, s->ld, scale, nullptr, 0, N, s->ws, need_grad ? s->emat : nullptr,
-                      st, fwd_ds, &sig))
-    return e;
+  {
+    ProfScope ps("fwd_tiles", st);
+    if (int e = run_fwd(LOSS_CLIP, s->img_rows, s->txt_all, sh, s->ld, scale, nullptr, 0, N, s->ws,
+                        need_grad ? s->emat : nullptr, st, fwd_ds, &sig))
+      return e;
+  }
+  ProfScope ps("fwd_reduce", st);
   const float2* row_part = reinterpret_cast<const float2*>(wsb + w.row_part);
   const long plane = (long)rank * 3 * N;
   reduce_rows_pub_kernel<<<ceil_div(n, 256), 256, 0, st>>>(row_part, f.total_chunks * 2, n, f.m_pad, s->peer.stats_peers,
@@ -1189,11 +1265,15 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
     const float* lse_row = s->lse2_row_all + (long)rank * n;
     mode = ranks > 1 ? (mrclip_step_uses_fwd_ds(s) ? 2 : 3) : (((long)n * N >= (1L << 22)) ? 1 : 0);
     float* msums = (d_scale && (mode == 0 || mode == 3)) ? s->msums : nullptr;
-    if (int e = mrclip_emat_check(sh, s->ws, lse_row, s->lse2_col_all, stream)) return e;
     const int* flag = mrclip_emat_flag(sh, s->ws);
-    if (int e = mrclip_clip_gwrite_if(s->img_rows, s->txt_all, sh, ld, lse_row, s->lse2_col_all, scale, 1.f, 1.f, s->ws, s->emat,
-                                      flag, stream))
-      return e;
+    {
+      ProfScope ps("emat_guard", st);
+      if (int e = mrclip_emat_check(sh, s->ws, lse_row, s->lse2_col_all, stream)) return e;
+      if (int e = mrclip_clip_gwrite_if(s->img_rows, s->txt_all, sh, ld, lse_row, s->lse2_col_all, scale, 1.f, 1.f, s->ws,
+                                        s->emat, flag, stream))
+        return e;
+    }
+    ProfScope ps("emat_transform", st);
     if (int e = mrclip_emat_transform(sh, s->ws, s->emat, lse_row, s->lse2_col_all, reinterpret_cast<const float*>(wsb + w.diag2),
                                       scale, 1.f, 1.f, flag, msums, 64, n, ranks, stream))
       return e;
@@ -1210,13 +1290,20 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
     xf.peer_n = n;
     xf.peer_rank = rank;
     xf.sig = pi;
-    if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws,
-                              const_cast<unsigned long long*>(s->peer.recv_peers), s->peer.recv_bf16 ? MRCLIP_DT_BF16 : MRCLIP_DT_F32,
-                              d, xf, st))
-      return e;
-    if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
-                              d_img_ld, DotArgs(), st))
-      return e;
+    {
+      ProfScope ps("gemm_dT_push", st);
+      if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws,
+                                const_cast<unsigned long long*>(s->peer.recv_peers),
+                                s->peer.recv_bf16 ? MRCLIP_DT_BF16 : MRCLIP_DT_F32, d, xf, st))
+        return e;
+    }
+    {
+      ProfScope ps("gemm_dI", st);
+      if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
+                                d_img_ld, DotArgs(), st))
+        return e;
+    }
+    ProfScope ps("sum_slots", st);
     const bool dot = (s->kind == 0 && d_scale && mode == 2);
     const long total = ((d & 3) == 0) ? (long)n * (d / 4) : (long)n * d;
     long blocks = (total + 255) / 256;
@@ -1235,14 +1322,19 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
       xf.dot_feat = s->img_rows;
       xf.dot_out = d_scale;
     }
-    if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
-                              d_img_ld, xf, st))
-      return e;
+    {
+      ProfScope ps("gemm_dI", st);
+      if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
+                                d_img_ld, xf, st))
+        return e;
+    }
+    ProfScope ps("gemm_dT", st);
     if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws, d_txt, d_txt_dtype,
                               d_txt_ld, DotArgs(), st))
       return e;
   }
   if (s->kind == 0 && d_scale) {
+    ProfScope ps("ds_finish", st);
     DsParams dp;
     memset(&dp, 0, sizeof dp);
     dp.mode = mode;
