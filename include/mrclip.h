@@ -252,6 +252,8 @@ typedef struct mrclip_step {
   float* lse2_col_all;     /* float [mrclip_padded_cols(N)] */
   float* msums;            /* float [64][2][ranks] */
   float* small;            /* float [mrclip_step_small_floats()], zeroed once */
+  float* inv_norm;         /* float [2][n] (image rows, text rows) for mrclip_step_forward(raw != 0); else may be NULL */
+  float* scale_buf;        /* float [1]: exp(logit_scale) written by a raw forward; else may be NULL */
   mrclip_peer peer;
 } mrclip_step;
 
@@ -261,9 +263,19 @@ size_t mrclip_step_small_floats(void);
  * fwd_ds), 0 when it uses the entropy sums of the rescale pass.  Pure function of the shape and mode. */
 int mrclip_step_uses_fwd_ds(const mrclip_step* s);
 /* img / txt: this rank's [n, d] feature rows (MRCLIP_DT_*, leading dims in elements).  scale (and bias, SigLIP, may be
- * NULL) are device scalars.  need_grad == 0: no E / G block is written.  loss_out: device float [1]. */
+ * NULL) are device scalars.  need_grad == 0: no E / G block is written.  loss_out: device float [1].
+ * raw != 0 (feature hand-off fusion, reference model.py:282-301, :324): img / txt are the towers' UN-normalised outputs
+ * and `scale` is the model's log-scale parameter; the pack pre-pass normalises the rows (F.normalize, eps 1e-12, fp32),
+ * keeps 1/||x|| in s->inv_norm and exp(scale) in s->scale_buf (which every later kernel of the step, and the backward,
+ * uses as the logit scale). */
 int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, long img_ld, const void* txt, int txt_dtype,
-                        long txt_ld, const float* scale, const float* bias, int need_grad, float* loss_out, void* stream);
+                        long txt_ld, const float* scale, const float* bias, int need_grad, int raw, float* loss_out,
+                        void* stream);
+/* Backward of the row normalisation, in place on a gradient block g [rows, d] (MRCLIP_DT_*, leading dim g_ld):
+ * g <- (g - y <g, y>) * inv_norm[row], y = the packed bf16 rows [rows, y_ld].  Chains d(loss)/d(normalised features),
+ * as mrclip_step_backward leaves it, to the tower outputs (autograd of F.normalize, model.py:282-301). */
+int mrclip_normalize_bwd(const void* y, long y_ld, const float* inv_norm, int rows, int d, void* g, int g_dtype, long g_ld,
+                         void* stream);
 /* coef: 1/(2n) (or 1/(2N) for ClipLoss(local_loss=False, gather_with_grad=False)); 1/n for SigLIP.  grad_out: device
  * float [1] or NULL.  d_img / d_txt: [n, d] of MRCLIP_DT_*; d_scale / d_bias: device float [1] or NULL. */
 int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* grad_out, float coef, void* d_img,

@@ -62,7 +62,8 @@ SIGNATURES = {
     "mrclip_peer_block_bytes": (C.c_size_t, []),
     "mrclip_step_small_floats": (C.c_size_t, []),
     "mrclip_step_uses_fwd_ds": (_I, [_P]),
-    "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _P, _P]),
+    "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _I, _P, _P]),
+    "mrclip_normalize_bwd": (_I, [_P, _L, _P, _I, _I, _P, _I, _L, _P]),
     "mrclip_step_backward": (_I, [_P, _P, _P, _F, _P, _I, _L, _P, _I, _L, _P, _P, _P]),
     "mrclip_prof_enable": (_I, [_I]),
     "mrclip_prof_report": (_I, [C.c_char_p, C.c_size_t]),

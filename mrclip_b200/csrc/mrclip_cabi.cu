@@ -1078,7 +1078,7 @@ int check_step(const mrclip_step* s) {
 }
 
 int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img_dtype, long img_ld, const void* txt,
-              int txt_dtype, long txt_ld, cudaStream_t st) {
+              int txt_dtype, long txt_ld, const float* log_scale, int raw, cudaStream_t st) {
   if (img_dtype < 0 || img_dtype > 2 || txt_dtype < 0 || txt_dtype > 2) return fail(-1, "step: bad feature dtype");
   if (img_ld < s->shape.d || txt_ld < s->shape.d) return fail(-1, "step: feature leading dimension < d");
   Pack2Params pp;
@@ -1098,6 +1098,15 @@ int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img
   pp.row0 = s->shape.label_offset;
   const int vec_ok = (img_ld % 8 == 0 && txt_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(txt) & 15) == 0) ? 1 : 0;
+  if (raw) {   // un-normalised tower outputs: one warp per row
+    if (!s->inv_norm || !s->scale_buf) return fail(-1, "step: raw forward needs inv_norm and scale_buf");
+    long blocks = (2L * pp.rows + 7) / 8;
+    if (blocks > 148L * 8) blocks = 148L * 8;
+    packnorm2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok, s->inv_norm, log_scale, s->scale_buf);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+  }
   const long total = 2L * pp.rows * (pp.ld / 8);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 8) blocks = 148L * 8;
@@ -1161,7 +1170,8 @@ int mrclip_step_uses_fwd_ds(const mrclip_step* s) {
 }
 
 int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, long img_ld, const void* txt, int txt_dtype,
-                        long txt_ld, const float* scale, const float* bias, int need_grad, float* loss_out, void* stream) {
+                        long txt_ld, const float* scale, const float* bias, int need_grad, int raw, float* loss_out,
+                        void* stream) {
   if (int e = check_step(s)) return e;
   if (!img || !txt || !scale || !loss_out) return fail(-1, "step_forward: NULL argument");
   if (need_grad && !s->emat) return fail(-1, "step_forward: need_grad without an E block");
@@ -1172,8 +1182,9 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
   const int ranks = pi.ranks, rank = pi.rank;
   {
     ProfScope ps("pack_push", st);
-    if (int e = step_pack(s, pi, img, img_dtype, img_ld, txt, txt_dtype, txt_ld, st)) return e;
+    if (int e = step_pack(s, pi, img, img_dtype, img_ld, txt, txt_dtype, txt_ld, scale, raw, st)) return e;
   }
+  if (raw) scale = s->scale_buf;     // exp(log-scale), written by the pack pre-pass
   FwdSig sig;
   if (ranks > 1) {
     sig.ready = pi.sig_local + CH_TEXT * kPeerMaxRanks;
@@ -1242,6 +1253,19 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
     scal_mean_kernel<<<1, 64, 0, st>>>(0, CH_LOSS, loss_out, pi);
     g_launches.fetch_add(1);
   }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_normalize_bwd(const void* y, long y_ld, const float* inv_norm, int rows, int d, void* g, int g_dtype, long g_ld,
+                         void* stream) {
+  if (!y || !inv_norm || !g || rows <= 0 || d <= 0 || y_ld < d || g_ld < d) return fail(-1, "normalize_bwd: bad arguments");
+  if (g_dtype < 0 || g_dtype > 2) return fail(-1, "bad dtype %d", g_dtype);
+  long blocks = ((long)rows + 7) / 8;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  normalize_bwd_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(y), y_ld, inv_norm,
+                                                                     rows, d, g, g_dtype, g_ld);
+  g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
 }

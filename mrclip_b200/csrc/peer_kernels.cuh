@@ -69,6 +69,89 @@ pack2_push_kernel(const Pack2Params p, const PeerInfo pi, int vec_ok) {
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Feature hand-off fusion (reference model.py:282-301, :324): pack2_push_kernel for UN-normalised tower
+// outputs.  One warp per (modality, row): y = x / max(||x||, 1e-12) in fp32 (F.normalize's definition), cast to bf16,
+// stored / pushed like the plain pack; 1/max(||x||, eps) is kept per row for the backward and the logit scale is
+// exponentiated once (scale_out[0] = exp(log_scale[0])).  Replaces two F.normalize passes, the autocast casts and
+// logit_scale.exp() in front of the loss.
+__global__ void __launch_bounds__(256)
+packnorm2_push_kernel(const Pack2Params p, const PeerInfo pi, int vec_ok, float* __restrict__ inv_norm,
+                      const float* __restrict__ log_scale, float* __restrict__ scale_out) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const int vpr = p.ld / 8;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && log_scale != nullptr) scale_out[0] = expf(log_scale[0]);
+  for (long w = blockIdx.x * (long)warps_per_block + (threadIdx.x >> 5); w < 2L * p.rows; w += (long)gridDim.x * warps_per_block) {
+    const bool is_txt = w >= p.rows;
+    const long r = is_txt ? w - p.rows : w;
+    const void* src = is_txt ? p.txt_src : p.img_src;
+    const int dt = is_txt ? p.txt_dtype : p.img_dtype;
+    const long sld = is_txt ? p.txt_src_ld : p.img_src_ld;
+    float ss = 0.f;
+    for (int c = lane; c < p.d; c += 32) {
+      const float v = load_as_float(src, dt, (size_t)(r * sld + c));
+      ss = fmaf(v, v, ss);
+    }
+    ss = warp_sum(ss);
+    const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    if (lane == 0) inv_norm[w] = inv;
+    for (int v8 = lane; v8 < vpr; v8 += 32) {
+      const int c = v8 * 8;
+      float f[8];
+      if (vec_ok && c + 8 <= p.d && dt == DT_F32) {
+        const float4 a = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * sld + c);
+        const float4 b = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + r * sld + c + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+      } else if (vec_ok && c + 8 <= p.d && dt == DT_BF16) {
+        const uint4 a = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(src) + r * sld + c);
+        const uint32_t u[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[2 * j] = __uint_as_float(u[j] << 16);
+          f[2 * j + 1] = __uint_as_float(u[j] & 0xffff0000u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = (c + j < p.d) ? load_as_float(src, dt, (size_t)(r * sld + c + j)) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= inv;
+      const uint4 o = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+      if (!is_txt) {
+        *reinterpret_cast<uint4*>(p.img_dst + r * p.ld + c) = o;
+      } else if (pi.ranks <= 1) {
+        *reinterpret_cast<uint4*>(p.txt_local + (p.row0 + r) * p.ld + c) = o;
+      } else {
+        for (int q = 0; q < pi.ranks; ++q)
+          *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(__ldg(p.txt_peers + q)) + (p.row0 + r) * p.ld + c) = o;
+      }
+    }
+  }
+  if (pi.ranks > 1) peer_signal_when_grid_done(pi, CH_TEXT, gridDim.x);
+}
+
+// Backward of the normalisation, in place on a gradient block: with y = x / ||x|| (the packed bf16 rows) and g = dL/dy,
+//   dL/dx = (g - y <g, y>) / ||x||.     One warp per row; g is [rows, d] of MRCLIP_DT_* with leading dimension g_ld.
+// Replaces the autograd of F.normalize (model.py:282-301) behind the loss.
+__global__ void __launch_bounds__(256)
+normalize_bwd_kernel(const __nv_bfloat16* __restrict__ y, long y_ld, const float* __restrict__ inv_norm, int rows, int d,
+                     void* __restrict__ g, int g_dtype, long g_ld) {
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  for (long r = blockIdx.x * (long)warps_per_block + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * warps_per_block) {
+    float dot = 0.f;
+    for (int c = lane; c < d; c += 32)
+      dot = fmaf(load_as_float(g, g_dtype, (size_t)(r * g_ld + c)), __bfloat162float(y[r * y_ld + c]), dot);
+    dot = warp_sum(dot);
+    const float inv = inv_norm[r];
+    for (int c = lane; c < d; c += 32) {
+      const size_t i = (size_t)(r * g_ld + c);
+      store_from_float(g, g_dtype, i, (load_as_float(g, g_dtype, i) - __bfloat162float(y[r * y_ld + c]) * dot) * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Forward reductions that publish straight into every rank's statistics block  stats[ranks][3][N]  (plane 0/1: per-column
 // (max2, sum) of the publisher's rows, plane 2: its row LSEs in [:n]).  reduce_rows_pub runs first, reduce_cols_pub
 // raises CH_STATS from its last block.  ranks == 1: plain local writes, no flag.

@@ -374,6 +374,10 @@ def _step_path_ok(eng, ws, world, need_grad):
     return True
 
 
+class _RawUnavailable(RuntimeError):
+    """forward_raw cannot run fused for this call (no whole-step path); the caller composes F.normalize + forward."""
+
+
 def _rows_major(x):
     x = x.detach()
     return x if x.stride(1) == 1 else x.contiguous()
@@ -563,7 +567,7 @@ def _lse_forward(eng, ws, image_features, text_features, scale, shape, rank, wor
 class _ClipLossFn(torch.autograd.Function):
     @staticmethod
     @_scoped
-    def forward(ctx, image_features, text_features, logit_scale, module):
+    def forward(ctx, image_features, text_features, logit_scale, module, raw=False):
         eng = _engine()
         _check_inputs(image_features, text_features)
         device = image_features.device
@@ -591,17 +595,22 @@ class _ClipLossFn(torch.autograd.Function):
                 ws.flip ^= 1
             loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
             plan.forward(eng, ws.flip if world > 1 else 0, _rows_major(image_features), _rows_major(text_features), scale,
-                         None, need_grad, loss)
+                         None, need_grad, loss, raw=raw)
             ws.has_emat = need_grad
             ctx.fast = (plan, ws.flip if world > 1 else 0)
+            ctx.raw = raw
             ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
             ctx.lease = module._pool.lease(ws)
-            ctx.scale = scale
+            ctx.scale = plan.scale_buf if raw else scale      # raw: exp(log-scale), written by the pack pre-pass
             ctx.in_dtypes = (image_features.dtype, text_features.dtype)
             ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
             if not need_grad:
                 ctx.lease.release()
             return loss
+        if raw:
+            ws.in_use = False
+            raise _RawUnavailable()
+        ctx.raw = False
         ctx.fwd_ds = bool(use_emat and world > 1 and module.local_loss and module.gather_with_grad
                           and ctx.needs_input_grad[1] and ctx.needs_input_grad[2]
                           and os.environ.get("MRCLIP_DS", "fwd").lower() != "entropy"
@@ -652,6 +661,10 @@ class _ClipLossFn(torch.autograd.Function):
             plan, flip = ctx.fast
             ds = torch.empty((1,), dtype=torch.float32, device=device) if need_s else None
             plan.backward(flip, ctx.scale, gout, coef, d_img, d_txt, ds, None)
+            if ctx.raw:       # chain to the un-normalised tower outputs and to the log-scale parameter
+                plan.normalize_bwd(flip, d_img, d_txt)
+                if need_s:
+                    ds = ds * ctx.scale
             ds_done = True
         elif ws.has_emat:
             gmat = ws.gmat_buffer(eng)
@@ -733,7 +746,7 @@ class _ClipLossFn(torch.autograd.Function):
             shp, dt = ctx.scale_meta
             d_scale = ds.reshape(shp).to(dt)
         ctx.lease.release()
-        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None
+        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, None, None
 
 
 class ClipLoss(nn.Module):
@@ -791,6 +804,19 @@ class ClipLoss(nn.Module):
 
     def forward(self, image_features, text_features, logit_scale, output_dict=False):
         total_loss = _ClipLossFn.apply(image_features, text_features, logit_scale, self)
+        return {"contrastive_loss": total_loss} if output_dict else total_loss
+
+    def forward_raw(self, image_embeds, text_embeds, log_logit_scale, output_dict=False):
+        """Feature hand-off fusion: the same loss taken from the towers' UN-normalised outputs and the
+        model's log-scale parameter -- ``forward(F.normalize(i), F.normalize(t), log_logit_scale.exp())`` of the reference
+        (model.py:282-301, :324 feeding loss.py:128-139) with the two normalisations, the casts and the exponential folded
+        into the pack pre-pass and their backward into one in-place pass over the gradients.  Falls back to exactly that
+        composition when the whole-step path is unavailable (CPU stand-in engine, MRCLIP_STEP=py, NCCL transports)."""
+        try:
+            total_loss = _ClipLossFn.apply(image_embeds, text_embeds, log_logit_scale, self, True)
+        except _RawUnavailable:
+            return self.forward(torch.nn.functional.normalize(image_embeds, dim=-1),
+                                torch.nn.functional.normalize(text_embeds, dim=-1), log_logit_scale.exp(), output_dict)
         return {"contrastive_loss": total_loss} if output_dict else total_loss
 
 
@@ -946,7 +972,7 @@ class MultiPositiveClipLoss(ClipLoss):
 class _SigLipLossFn(torch.autograd.Function):
     @staticmethod
     @_scoped
-    def forward(ctx, image_features, text_features, logit_scale, logit_bias, module):
+    def forward(ctx, image_features, text_features, logit_scale, logit_bias, module, raw=False):
         eng = _engine()
         _check_inputs(image_features, text_features)
         device = image_features.device
@@ -966,9 +992,14 @@ class _SigLipLossFn(torch.autograd.Function):
             if world > 1:
                 ws.flip ^= 1
             plan.forward(eng, ws.flip if world > 1 else 0, _rows_major(image_features), _rows_major(text_features), scale,
-                         bias, any(ctx.needs_input_grad), loss)
+                         bias, any(ctx.needs_input_grad), loss, raw=raw)
             ws.has_emat = any(ctx.needs_input_grad)
             ctx.fast = (plan, ws.flip if world > 1 else 0)
+            if raw:
+                scale = plan.scale_buf
+        elif raw:
+            ws.in_use = False
+            raise _RawUnavailable()
         else:
             _gather_packed(eng, ws, image_features, text_features, rank, world,
                            gather_images=not use_emat and any(ctx.needs_input_grad))
@@ -982,7 +1013,7 @@ class _SigLipLossFn(torch.autograd.Function):
             eng.siglip_fwd(ws.img_all[rows], ws.txt_all, shape, scale, bias, ws.scratch, loss)
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
         ctx.lease = module._pool.lease(ws)
-        ctx.scale, ctx.bias = scale, bias
+        ctx.scale, ctx.bias, ctx.raw = scale, bias, raw
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         ctx.bias_meta = (logit_bias.shape, logit_bias.dtype) if torch.is_tensor(logit_bias) else None
@@ -1013,6 +1044,10 @@ class _SigLipLossFn(torch.autograd.Function):
         if ctx.fast is not None:
             plan, flip = ctx.fast
             plan.backward(flip, ctx.scale, gout, coef, d_img, d_txt, ds, db)
+            if ctx.raw:
+                plan.normalize_bwd(flip, d_img, d_txt)
+                if need_s:
+                    ds = ds * ctx.scale
         elif ws.has_emat:
             gmat = ws.gmat_buffer(eng)
             eng.siglip_e_scalars(shape, ws.scratch, coef, gout, ds, db, False)
@@ -1047,7 +1082,7 @@ class _SigLipLossFn(torch.autograd.Function):
             shp, dt = ctx.bias_meta
             d_bias = db.reshape(shp).to(dt)
         ctx.lease.release()
-        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, d_bias, None
+        return (d_img if need_i else None), (d_txt if need_t else None), d_scale, d_bias, None, None
 
 
 class SigLipLoss(nn.Module):
@@ -1095,4 +1130,15 @@ class SigLipLoss(nn.Module):
 
     def forward(self, image_features, text_features, logit_scale, logit_bias, output_dict=False):
         loss = _SigLipLossFn.apply(image_features, text_features, logit_scale, logit_bias, self)
+        return {"contrastive_loss": loss} if output_dict else loss
+
+    def forward_raw(self, image_embeds, text_embeds, log_logit_scale, logit_bias, output_dict=False):
+        """``forward(F.normalize(i), F.normalize(t), log_logit_scale.exp(), logit_bias)`` with the normalisations, casts and
+        the exponential fused into the pack pre-pass (see ``ClipLoss.forward_raw``)."""
+        try:
+            loss = _SigLipLossFn.apply(image_embeds, text_embeds, log_logit_scale, logit_bias, self, True)
+        except _RawUnavailable:
+            return self.forward(torch.nn.functional.normalize(image_embeds, dim=-1),
+                                torch.nn.functional.normalize(text_embeds, dim=-1), log_logit_scale.exp(), logit_bias,
+                                output_dict)
         return {"contrastive_loss": loss} if output_dict else loss

@@ -31,7 +31,7 @@ class Step(C.Structure):
     _fields_ = [("shape", Shape), ("ld", C.c_int), ("kind", C.c_int), ("local_loss", C.c_int), ("img_rows", C.c_void_p),
                 ("txt_all", C.c_void_p), ("ws", C.c_void_p), ("emat", C.c_void_p), ("stats", C.c_void_p),
                 ("lse2_row_all", C.c_void_p), ("lse2_col_all", C.c_void_p), ("msums", C.c_void_p), ("small", C.c_void_p),
-                ("peer", Peer)]
+                ("inv_norm", C.c_void_p), ("scale_buf", C.c_void_p), ("peer", Peer)]
 
 
 KIND_CLIP, KIND_SIGLIP = 0, 1
@@ -52,6 +52,8 @@ class StepPlan:
         dev = ws.img_all.device
         self.small = torch.zeros(int(self.lib.mrclip_step_small_floats()), dtype=torch.float32, device=dev)
         self.ctl = torch.zeros(64, dtype=torch.int32, device=dev)
+        self.inv_norm = torch.zeros((2, ws.n), dtype=torch.float32, device=dev)      # raw forward: 1/||x|| of every row
+        self.scale_buf = torch.zeros((1,), dtype=torch.float32, device=dev)          # raw forward: exp(log-scale)
         rows = slice(rank * ws.n, (rank + 1) * ws.n)
         self.steps = []
         for flip in ((0, 1) if ws.world > 1 else (0,)):
@@ -63,6 +65,7 @@ class StepPlan:
             st.emat = None
             st.lse2_row_all, st.lse2_col_all = ws.lse2_row_all.data_ptr(), ws.lse2_col_all.data_ptr()
             st.msums, st.small = ws.msums.data_ptr(), self.small.data_ptr()
+            st.inv_norm, st.scale_buf = self.inv_norm.data_ptr(), self.scale_buf.data_ptr()
             if ws.world > 1:
                 txt, _, txt_ptrs = ws.sym["txt"][flip]
                 stats, _, stats_ptrs = ws.sym["stats"]
@@ -91,14 +94,23 @@ class StepPlan:
                 st.peer.recv_bf16 = int(recv.dtype == torch.bfloat16)
         return True
 
-    def forward(self, eng, flip, img, txt, scale, bias, need_grad, loss_out):
+    def forward(self, eng, flip, img, txt, scale, bias, need_grad, loss_out, raw=False):
         st = self.steps[flip]
         if need_grad and not st.emat and not self._attach_grad_buffers(eng):
             raise RuntimeError("mrclip_b200: peer receive buffers unavailable")
         _cabi.check(self.lib.mrclip_step_forward(C.byref(st), img.data_ptr(), _DT[img.dtype], img.stride(0), txt.data_ptr(),
                                                  _DT[txt.dtype], txt.stride(0), scale.data_ptr(), _ptr(bias),
-                                                 int(bool(need_grad)), loss_out.data_ptr(),
+                                                 int(bool(need_grad)), int(bool(raw)), loss_out.data_ptr(),
                                                  torch.cuda.current_stream().cuda_stream))
+
+    def normalize_bwd(self, flip, d_img, d_txt):
+        """Chain the gradients of the normalised features (as backward leaves them) to the raw tower outputs, in place."""
+        ws, st = self.ws, self.steps[flip]
+        stream = torch.cuda.current_stream().cuda_stream
+        txt_rows = st.txt_all + self.rank * ws.n * ws.ld * 2
+        for y, inv, g in ((st.img_rows, self.inv_norm[0], d_img), (txt_rows, self.inv_norm[1], d_txt)):
+            _cabi.check(self.lib.mrclip_normalize_bwd(y, ws.ld, inv.data_ptr(), ws.n, ws.d, g.data_ptr(), _DT[g.dtype],
+                                                      g.stride(0), stream))
 
     def backward(self, flip, scale, grad_out, coef, d_img, d_txt, d_scale, d_bias):
         st = self.steps[flip]

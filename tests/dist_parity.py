@@ -10,6 +10,8 @@ loss (1e-3), feature gradients (1e-2, norm-wise), d logit_scale / d logit_bias (
 
     c3       ClipLoss (T,T)            N=32768 D=768      (configs[2], the headline)
     c2       ClipLoss all four modes   N=4096  D=512      (configs[1]; (F,T) and (T,T) are the ones it names)
+    c2raw    ClipLoss.forward_raw      N=4096  D=512      (un-normalised fp32 features, log-scale)
+    c4raw    SigLipLoss.forward_raw    N=4096  D=768
     c4       SigLipLoss + logit_bias   N=16384 D=768      (configs[3])
     mpos     MultiPositiveClipLoss     N=8192  D=512      (512 label classes)
     ragged   ClipLoss (T,T)            n=1000 per rank, D=200 (no tile / vector alignment anywhere)
@@ -36,6 +38,9 @@ CASES = {
     # (weakly correlated pairs: at scale 100 the usual 0.5 mix saturates the loss to ~1e-30 and every gradient to 0)
     "c2s100": dict(kind="clip", N=4096, D=512, scale=100.0, modes=[(True, True)], grad_output=65536.0, corr=0.06),
     "c4": dict(kind="siglip", N=16384, D=768, scale=10.0, bias=-10.0),
+    # feature hand-off fusion (forward_raw): un-normalised fp32 tower outputs + log-scale parameter
+    "c2raw": dict(kind="clip", N=4096, D=512, scale=2.659, modes=[(True, True), (False, True)], raw=True),
+    "c4raw": dict(kind="siglip", N=4096, D=768, scale=2.3026, bias=-10.0, raw=True),
     "mpos": dict(kind="mpos", N=8192, D=512, scale=14.285714, classes=512, delta=0.3),
     "ragged": dict(kind="clip", n=1000, D=200, scale=30.0, modes=[(True, True), (False, True)], corr=0.2),
 }
@@ -68,6 +73,11 @@ def main():
             continue
         n, D = N // world, c["D"]
         img, txt = features(N, D, 1234 + len(name) + N, dev, c.get("corr", 0.5))
+        raw = bool(c.get("raw", False))
+        if raw:     # un-normalised rows of varying length, fp32 (what a tower hands over under AMP)
+            g = torch.Generator().manual_seed(99)
+            img = img.float() * (0.5 + 4.0 * torch.rand(N, 1, generator=g).to(dev))
+            txt = txt.float() * (0.5 + 4.0 * torch.rand(N, 1, generator=g).to(dev))
         rows = slice(rank * n, (rank + 1) * n)
         go = float(c.get("grad_output", 1.0))
         modes = c.get("modes", [(True, True)])
@@ -81,16 +91,17 @@ def main():
                 if c["kind"] == "clip":
                     ll, gg = mode
                     mod = ClipLoss(local_loss=ll, gather_with_grad=gg, cache_labels=True, rank=rank, world_size=world)
-                    loss = mod(i, t, s)
+                    loss = mod.forward_raw(i, t, s) if raw else mod(i, t, s)
                     if ref is None:
-                        ref = torch_ref.clip_reference(img[rows], txt[rows], c["scale"], ll, gg, rank, world, go)
+                        ref = torch_ref.clip_reference(img[rows], txt[rows], c["scale"], ll, gg, rank, world, go, raw=raw)
                     nl = n if (world > 1 and ll) else N
                     labels_ok = torch.equal(mod.get_ground_truth(dev, nl), ref["labels"])
                 elif c["kind"] == "siglip":
                     b = torch.tensor(c["bias"], device=dev, requires_grad=True)
-                    loss = SigLipLoss(rank=rank, world_size=world)(i, t, s, b)
+                    sl = SigLipLoss(rank=rank, world_size=world)
+                    loss = sl.forward_raw(i, t, s, b) if raw else sl(i, t, s, b)
                     if ref is None:
-                        ref = torch_ref.siglip_reference(img[rows], txt[rows], c["scale"], c["bias"], rank, world, go)
+                        ref = torch_ref.siglip_reference(img[rows], txt[rows], c["scale"], c["bias"], rank, world, go, raw=raw)
                     labels_ok = True
                 else:
                     lab = torch.randint(0, c["classes"], (N,), generator=torch.Generator().manual_seed(7)).to(dev)

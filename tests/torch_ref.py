@@ -38,12 +38,22 @@ def _finish(loss, leaves, grad_output):
     return out
 
 
-def clip_reference(image, text, scale, local_loss=False, gather_with_grad=False, rank=0, world=1, grad_output=1.0):
+def _leaves(image, text, scale, raw):
+    """Leaf tensors and what the loss sees.  raw: the leaves are the towers' un-normalised outputs and the model's
+    log-scale parameter; the loss sees F.normalize(.) and scale.exp() (model.py:282-301, :324), gradients flow back."""
+    i0 = image.detach().float().clone().requires_grad_(True)
+    t0 = text.detach().float().clone().requires_grad_(True)
+    s0 = torch.as_tensor(scale, dtype=torch.float32, device=i0.device).detach().clone().requires_grad_(True)
+    if raw:
+        return (i0, t0, s0), (F.normalize(i0, dim=-1), F.normalize(t0, dim=-1), s0.exp())
+    return (i0, t0, s0), (i0, t0, s0)
+
+
+def clip_reference(image, text, scale, local_loss=False, gather_with_grad=False, rank=0, world=1, grad_output=1.0,
+                   raw=False):
     """One rank's ClipLoss forward + backward in fp32 torch.  image/text: this rank's [n, D] rows (any float dtype,
     up-cast to fp32).  Returns dict(loss, d_image, d_text, d_scale) of fp32 tensors on the same device."""
-    i = image.detach().float().clone().requires_grad_(True)
-    t = text.detach().float().clone().requires_grad_(True)
-    s = torch.as_tensor(scale, dtype=torch.float32, device=i.device).detach().clone().requires_grad_(True)
+    (i0, t0, s0), (i, t, s) = _leaves(image, text, scale, raw)
     n = i.shape[0]
     if world > 1:
         all_i = _gather(i, world, gather_with_grad, local_loss, rank)
@@ -62,18 +72,16 @@ def clip_reference(image, text, scale, local_loss=False, gather_with_grad=False,
     if world > 1 and local_loss:
         labels = labels + num * rank
     loss = (F.cross_entropy(logits_per_image, labels) + F.cross_entropy(logits_per_text, labels)) / 2
-    out = _finish(loss, {"image": i, "text": t, "scale": s}, grad_output)
+    out = _finish(loss, {"image": i0, "text": t0, "scale": s0}, grad_output)
     out["labels"] = labels
     return out
 
 
-def siglip_reference(image, text, scale, bias, rank=0, world=1, grad_output=1.0):
+def siglip_reference(image, text, scale, bias, rank=0, world=1, grad_output=1.0, raw=False):
     """One rank's SigLipLoss: its image rows against every rank's text chunk, positives in its own chunk only; the text
     features travel with gradient (the reference's neighbour exchanges are ``*_with_grad``, loss.py:279-311)."""
-    i = image.detach().float().clone().requires_grad_(True)
-    t = text.detach().float().clone().requires_grad_(True)
-    s = torch.as_tensor(scale, dtype=torch.float32, device=i.device).detach().clone().requires_grad_(True)
-    leaves = {"image": i, "text": t, "scale": s}
+    (i0, t0, s0), (i, t, s) = _leaves(image, text, scale, raw)
+    leaves = {"image": i0, "text": t0, "scale": s0}
     b = None
     if bias is not None:
         b = torch.as_tensor(bias, dtype=torch.float32, device=i.device).detach().clone().requires_grad_(True)
