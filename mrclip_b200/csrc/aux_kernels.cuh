@@ -328,7 +328,7 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
                       int ncb, const float* __restrict__ lse2_row, const float* __restrict__ lse2_col,
                       const float* __restrict__ diag2, int label_offset, float w_row, float w_col,
                       const int* __restrict__ skip_if, float* __restrict__ msums_all, int n_per_rank, int ranks,
-                      int msum_slots) {
+                      int msum_slots, int band0) {
   if (skip_if != nullptr && __ldg(skip_if) != 0) return;
   // the per-block sums are spread over msum_slots copies of [2][ranks] (the caller adds them up): thousands of
   // blocks adding into one address serialise in L2 and cost more than the pass itself
@@ -336,7 +336,7 @@ emat_transform_kernel(uint16_t* __restrict__ emat, long ld, int m_rows, int n_pa
   __shared__ __align__(16) float cfac[1024];
   __shared__ __align__(16) float lcol[WSUM ? 1024 : 4];
   __shared__ float bacc[2][64];   // per-block sums by column owner (ranks <= 64)
-  const int band = blockIdx.y;
+  const int band = blockIdx.y + band0;     // (a launch may cover a sub-range of the 32-row bands)
   const int col0 = blockIdx.x * 1024;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* cw_row = colc + (size_t)band * ncb;

@@ -877,12 +877,12 @@ int mrclip_clip_gwrite_if(const void* a_rows, const void* b_all, mrclip_shape sh
                     run_if, (cudaStream_t)stream);
 }
 
-int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
-                          const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
-                          float* msums, int msum_slots, int n_per_rank, int ranks, void* stream) {
+// bands [band0, band0 + nbands) of 32 rows each (nbands <= 0: all of them); zero_msums: clear the sums first
+static int run_emat_transform(const mrclip_shape& sh, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
+                       const float* diag2, float w_row, float w_col, const int* skip_if, float* msums, int msum_slots,
+                       int n_per_rank, int ranks, int band0, int nbands, bool zero_msums, cudaStream_t st) {
   if (int e = check_shape(sh, mrclip_padded_dim(sh.d))) return e;
   if (!emat || !lse2_row || !lse2_col || !diag2) return fail(-1, "emat_transform: NULL argument");
-  (void)scale;
   if (msums && msum_slots <= 0) return fail(-1, "emat_transform: msum_slots must be positive");
   if (msums && (ranks > 64 || (ranks > 1 && n_per_rank < 8)))
     return fail(-1, "emat_transform: split sums need ranks <= 64 and n_per_rank >= 8 (got %d x %d)", ranks, n_per_rank);
@@ -891,15 +891,19 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
   const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
   const WsLayout w = ws_layout(sh.m_rows, sh.n_cols, sh.d);
   const float* colc = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ws) + w.col_c);
-  dim3 grid(ceil_div(f.n_pad, 1024), f.bands);
-  cudaStream_t st = (cudaStream_t)stream;
+  if (nbands <= 0) {
+    band0 = 0;
+    nbands = f.bands;
+  }
+  if (band0 < 0 || band0 + nbands > f.bands) return fail(-1, "emat_transform: bad band range");
+  dim3 grid(ceil_div(f.n_pad, 1024), nbands);
   if (msums) {
-    CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks * msum_slots, st));
+    if (zero_msums) CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks * msum_slots, st));
     emat_transform_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
                                                       f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
                                                       sh.label_offset, w_row, w_col, skip_if, msums, n_per_rank, ranks,
-                                                      msum_slots);
-    if (skip_if) {   // guard raised: the sums come from the exact recompute's partials instead
+                                                      msum_slots, band0);
+    if (skip_if && band0 + nbands == f.bands) {   // guard raised: the sums come from the exact recompute's partials instead
       const int items = f.num_rb * f.total_chunks;
       emat_fallback_sums_kernel<<<ceil_div(items, 256), 256, 0, st>>>(
           skip_if, reinterpret_cast<const float2*>(reinterpret_cast<const uint8_t*>(ws) + w.sc_part), f.num_rb,
@@ -909,11 +913,19 @@ int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* ls
   } else {
     emat_transform_kernel<false><<<grid, 256, 0, st>>>(reinterpret_cast<uint16_t*>(emat), (long)f.n_pad, sh.m_rows,
                                                        f.n_pad, colc, f.n_pad / 64, lse2_row, lse2_col, diag2,
-                                                       sh.label_offset, w_row, w_col, skip_if, nullptr, 1, 1, 1);
+                                                       sh.label_offset, w_row, w_col, skip_if, nullptr, 1, 1, 1, band0);
   }
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
   return 0;
+}
+
+extern "C" int mrclip_emat_transform(mrclip_shape sh, void* ws, void* emat, const float* lse2_row, const float* lse2_col,
+                                     const float* diag2, const float* scale, float w_row, float w_col, const int* skip_if,
+                                     float* msums, int msum_slots, int n_per_rank, int ranks, void* stream) {
+  (void)scale;
+  return run_emat_transform(sh, ws, emat, lse2_row, lse2_col, diag2, w_row, w_col, skip_if, msums, msum_slots, n_per_rank,
+                            ranks, 0, 0, true, (cudaStream_t)stream);
 }
 
 int mrclip_gmat_gemm_dot(int transposed, const void* gmat, mrclip_shape shape, const void* feat, int ld, float coef,
@@ -1116,6 +1128,42 @@ int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img
   return 0;
 }
 
+// Second stream + events of the banded backward (rescale pass of band b+1 overlapped with the dI GEMM of band b).
+// One set per device, created on first use; fork / join through events only, so the pattern is graph-capturable.
+constexpr int kMaxBands = 16;
+struct SideStream {
+  cudaStream_t st = nullptr;
+  cudaEvent_t fork = nullptr, ev[kMaxBands] = {};
+};
+SideStream* side_stream() {
+  static std::mutex mu;
+  static std::map<int, SideStream*> per_dev;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = per_dev.find(dev);
+  if (it != per_dev.end()) return it->second;
+  SideStream* s = new SideStream();
+  bool ok = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < kMaxBands; ++i) ok = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    delete s;
+    s = nullptr;
+  }
+  per_dev[dev] = s;
+  return s;
+}
+// Row bands of the backward: the rescale pass is HBM-bound and the dI GEMM tensor-bound, so band b+1 is rescaled on the
+// side stream while band b is contracted.  MRCLIP_BANDS overrides (1 = off).
+int pick_bands(int n) {
+  if (const char* e = getenv("MRCLIP_BANDS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= kMaxBands) return v;
+  }
+  return n >= 16384 ? 8 : (n >= 8192 ? 4 : 1);
+}
+
 int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pass's entropy sums on every shape
   const char* e = getenv("MRCLIP_DS");
   return (e && strcmp(e, "entropy") == 0) ? 1 : 0;
@@ -1284,7 +1332,8 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
   const WsLayout w = ws_layout(n, N, d);
   uint8_t* wsb = reinterpret_cast<uint8_t*>(s->ws);
   const __nv_bfloat16* txt_rows = reinterpret_cast<const __nv_bfloat16*>(s->txt_all) + (size_t)rank * n * ld;
-  int mode = -1;
+  int mode = -1, nbands = 1, band_rows = n;
+  SideStream* ss = nullptr;
   if (s->kind == 0) {
     const float* lse_row = s->lse2_row_all + (long)rank * n;
     mode = ranks > 1 ? (mrclip_step_uses_fwd_ds(s) ? 2 : 3) : (((long)n * N >= (1L << 22)) ? 1 : 0);
@@ -1297,35 +1346,76 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
                                         s->emat, flag, stream))
         return e;
     }
-    ProfScope ps("emat_transform", st);
-    if (int e = mrclip_emat_transform(sh, s->ws, s->emat, lse_row, s->lse2_col_all, reinterpret_cast<const float*>(wsb + w.diag2),
-                                      scale, 1.f, 1.f, flag, msums, 64, n, ranks, stream))
-      return e;
+    nbands = pick_bands(n);
+    ss = nbands > 1 ? side_stream() : nullptr;
+    if (ss == nullptr) nbands = 1;
+    if (nbands > 1) {
+      band_rows = ceil_div(ceil_div(n, nbands), 256) * 256;
+      nbands = ceil_div(n, band_rows);
+    }
+    if (nbands <= 1) {
+      ProfScope ps("emat_transform", st);
+      if (int e = run_emat_transform(sh, s->ws, s->emat, lse_row, s->lse2_col_all, reinterpret_cast<const float*>(wsb + w.diag2),
+                                     1.f, 1.f, flag, msums, 64, n, ranks, 0, 0, true, st))
+        return e;
+    } else {
+      // fork: the side stream rescales band after band, an event per band tells the GEMMs below when theirs is ready
+      if (msums) CUDA_TRY(cudaMemsetAsync(msums, 0, sizeof(float) * 2 * ranks * 64, st));
+      CUDA_TRY(cudaEventRecord(ss->fork, st));
+      CUDA_TRY(cudaStreamWaitEvent(ss->st, ss->fork, 0));
+      ProfScope ps("emat_transform", ss->st);
+      for (int b = 0; b < nbands; ++b) {
+        const int r0 = b * band_rows, r1 = r0 + band_rows < n ? r0 + band_rows : n;
+        if (int e = run_emat_transform(sh, s->ws, s->emat, lse_row, s->lse2_col_all,
+                                       reinterpret_cast<const float*>(wsb + w.diag2), 1.f, 1.f, flag, msums, 64, n, ranks,
+                                       r0 / 32, ceil_div(r1 - r0, 32), false, ss->st))
+          return e;
+        CUDA_TRY(cudaEventRecord(ss->ev[b], ss->st));
+      }
+    }
     if (ranks > 1 && msums) {
+      if (nbands > 1) CUDA_TRY(cudaStreamWaitEvent(st, ss->ev[nbands - 1], 0));
       msums_pub_kernel<<<1, 64, 0, st>>>(msums, 64, s->small + kSmallR2Row, pi);
       g_launches.fetch_add(1);
     }
   } else {
     if (int e = mrclip_siglip_e_scalars(sh, s->ws, coef, grad_out, d_scale, d_bias, 0, stream)) return e;
   }
+  // dI = G . T_all, band by band (each band waits for its rescale on the side stream)
+  auto run_di = [&](const DotArgs& xf0) -> int {
+    ProfScope ps("gemm_dI", st);
+    const size_t esz = d_img_dtype == MRCLIP_DT_F32 ? 4 : 2;
+    const size_t g_ld = (size_t)mrclip_padded_cols(N);
+    for (int b = 0; b < nbands; ++b) {
+      const int r0 = b * band_rows, r1 = r0 + band_rows < n ? r0 + band_rows : n;
+      if (nbands > 1) CUDA_TRY(cudaStreamWaitEvent(st, ss->ev[b], 0));
+      DotArgs xf = xf0;
+      if (xf.dot_feat) xf.dot_feat = reinterpret_cast<const uint8_t*>(xf0.dot_feat) + (size_t)r0 * ld * 2;
+      if (int e = run_gmat_gemm(false, reinterpret_cast<uint8_t*>(s->emat) + (size_t)r0 * g_ld * 2, r1 - r0, N, s->txt_all, d, ld,
+                                coef, scale, grad_out, s->ws, reinterpret_cast<uint8_t*>(d_img) + (size_t)r0 * d_img_ld * esz,
+                                d_img_dtype, d_img_ld, xf, st))
+        return e;
+    }
+    return 0;
+  };
   if (ranks > 1) {
     DotArgs xf;
     xf.peer = s->peer.recv_peers;
     xf.peer_n = n;
     xf.peer_rank = rank;
     xf.sig = pi;
-    {
+    auto run_dt_push = [&]() -> int {
       ProfScope ps("gemm_dT_push", st);
-      if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws,
-                                const_cast<unsigned long long*>(s->peer.recv_peers),
-                                s->peer.recv_bf16 ? MRCLIP_DT_BF16 : MRCLIP_DT_F32, d, xf, st))
-        return e;
-    }
-    {
-      ProfScope ps("gemm_dI", st);
-      if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
-                                d_img_ld, DotArgs(), st))
-        return e;
+      return run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws,
+                           const_cast<unsigned long long*>(s->peer.recv_peers),
+                           s->peer.recv_bf16 ? MRCLIP_DT_BF16 : MRCLIP_DT_F32, d, xf, st);
+    };
+    if (nbands > 1) {   // large row blocks: hide the rescale pass behind the dI bands, then push
+      if (int e = run_di(DotArgs())) return e;
+      if (int e = run_dt_push()) return e;
+    } else {            // small row blocks: push first, so that the NVLink transfers drain under the dI GEMM
+      if (int e = run_dt_push()) return e;
+      if (int e = run_di(DotArgs())) return e;
     }
     ProfScope ps("sum_slots", st);
     const bool dot = (s->kind == 0 && d_scale && mode == 2);
@@ -1346,12 +1436,7 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
       xf.dot_feat = s->img_rows;
       xf.dot_out = d_scale;
     }
-    {
-      ProfScope ps("gemm_dI", st);
-      if (int e = run_gmat_gemm(false, s->emat, n, N, s->txt_all, d, ld, coef, scale, grad_out, s->ws, d_img, d_img_dtype,
-                                d_img_ld, xf, st))
-        return e;
-    }
+    if (int e = run_di(xf)) return e;
     ProfScope ps("gemm_dT", st);
     if (int e = run_gmat_gemm(true, s->emat, n, N, s->img_rows, d, ld, coef, scale, grad_out, s->ws, d_txt, d_txt_dtype,
                               d_txt_ld, DotArgs(), st))
