@@ -243,8 +243,6 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   off += align_up((size_t)f.total_chunks * 2 * f.m_pad * sizeof(float2), 256);
   w.col_l = off;
   off += align_up((size_t)f.bands * f.n_pad * sizeof(float), 256);
-  w.diag2 = off;
-  off += align_up((size_t)f.m_pad * sizeof(float), 256);
   const size_t fwd_end = off;
   // backward view (aliases the forward view; forward partials are dead by then)
   w.dpart = 0;
@@ -275,6 +273,10 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
   // MODE_FWDEU: u of every (row, slot); appended so that every other offset stays where it was
   w.row_ent = off;
   off += align_up((size_t)f.total_chunks * 2 * f.m_pad * sizeof(float), 256);
+  // positive logits of this rank's rows: read by the rescale pass, which may run (banded, on the side stream) while
+  // a gradient GEMM already writes its split-K partials over the forward view -> kept outside the aliased region
+  w.diag2 = off;
+  off += align_up((size_t)f.m_pad * sizeof(float), 256);
   w.total = off;
   return w;
 }
@@ -1161,7 +1163,8 @@ int pick_bands(int n) {
     const int v = atoi(e);
     if (v >= 1 && v <= kMaxBands) return v;
   }
-  return n >= 16384 ? 8 : (n >= 8192 ? 4 : 1);
+  (void)n;
+  return 1;   // measured on B200 (profiles/r2/r2c_*): no gain yet -- the two kernels contend for the SMs' registers
 }
 
 int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pass's entropy sums on every shape
