@@ -48,7 +48,11 @@ constexpr float kLn2 = 0.6931471805599453f;
 //        weighted logit sum, merged online like the LSE).  With it d logit_scale of a multi-rank local loss needs no
 //        entropy arithmetic in the rescale pass:  s dL_r/ds = <dT_r, T_r> + ln2/(2n) * (R2(r,*) - R2(*,r)),
 //        R2(q, r) = sum over rows of q and columns of r of Prow * S2  (not validated on hardware yet; MRCLIP_DS=fwd).
-enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2, MODE_FWDE = 3, MODE_FWDEU = 4 };
+// RANK:  retrieval metrics (reference train.py:465-534, get_clip_metrics): the same S tiles with a rank-of-label epilogue
+//        instead of the LSE.  Phase 0 scatters every row's positive logits (columns of the row's class) into a CSR list;
+//        phase 1 counts, per row, the negatives above its best positive and, for 32 positives at a time held in
+//        registers, the (negative, positive) pairs with negative > positive.  No N x N matrix, no sort.
+enum : int { MODE_FWD = 0, MODE_BWD = 1, MODE_GW = 2, MODE_FWDE = 3, MODE_FWDEU = 4, MODE_RANK = 5 };
 enum : int { LOSS_CLIP = 0, LOSS_SIGLIP = 1 };
 
 struct TileParams {
@@ -90,6 +94,17 @@ struct TileParams {
   // source rank q were stored into this rank's buffer by q's pack2_push_kernel; a column tile may be loaded once
   // sig_ready[q] has reached *sig_epoch (peer_sync.cuh, CH_TEXT).  The chunk order is rotated so that the tiles on this
   // rank's own columns -- which wait for nobody -- run first, then the sources in ring order.
+  // RANK (retrieval metrics)
+  const int* rk_row_cls;   // [m_rows] dense class id of each row
+  const int* rk_col_cls;   // [n_pad]  dense class id of each column (-1 in the padding)
+  const int* rk_col_ord;   // [n_pad]  ordinal of column j among the columns of its class
+  const long long* rk_off; // [m_rows] start of row i's positive list
+  const int* rk_m;         // [m_rows] number of positives of row i
+  float* rk_pos;           // positive logits (raw cosines): rk_pos[rk_off[i] + rk_col_ord[j]] = C_ij
+  const float* rk_lmax;    // [m_rows] phase 1: largest positive of the row
+  unsigned long long* rk_pairs;   // [m_rows] phase 1: += #{(k negative, t positive in this chunk): C_ik > C_it}
+  int* rk_best;            // [m_rows] phase 1 (chunk 0 only): += #{k negative: C_ik > lmax_i}
+  int rk_phase, rk_chunk0;
   const int* sig_ready; // this rank's sig block, CH_TEXT row; null: B is complete at launch
   const int* sig_epoch; // this rank's epoch of CH_TEXT
   int src_cols;         // columns per source rank
@@ -402,7 +417,26 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       float u_run = 0.f;                         // FWDEU: running sum of 2^(S2 - m_run) * S2
       float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;  // scalar partials (loss | ds, db)
       float lr2 = CUDART_INF_F;
-      if (!kFwd && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
+      if (!kFwd && MODE != MODE_RANK && LOSS == LOSS_CLIP && row_valid) lr2 = __ldg(p.lse2_a + grow);
+      // RANK: this row's class, list offset and (phase 1) the 32 positives of the current chunk, +inf padded
+      int rk_cls = -2, rk_nbest = 0;
+      long long rk_off = 0;
+      unsigned long long rk_npairs = 0ull;
+      float rk_lmax = CUDART_INF_F, rk_lmin = CUDART_INF_F;
+      float rk_l[MODE == MODE_RANK ? 32 : 1];
+      if (MODE == MODE_RANK && row_valid) {
+        rk_cls = __ldg(p.rk_row_cls + grow);
+        rk_off = __ldg(p.rk_off + grow);
+        if (p.rk_phase == 1) {
+          const int m = __ldg(p.rk_m + grow);
+          rk_lmax = p.rk_chunk0 == 0 ? __ldg(p.rk_lmax + grow) : CUDART_INF_F;    // best counted once, in chunk 0
+#pragma unroll
+          for (int t = 0; t < 32; ++t) {
+            rk_l[t] = (p.rk_chunk0 + t < m) ? p.rk_pos[rk_off + p.rk_chunk0 + t] : CUDART_INF_F;
+            rk_lmin = fminf(rk_lmin, rk_l[t]);
+          }
+        }
+      }
 
       for (int t = t0; t < t1; ++t) {
         const uint32_t buf = s_use % NSB, use = s_use / NSB;
@@ -547,6 +581,30 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           p.col_l[(size_t)band * p.n_pad + col_base + lane] = cs[0];
           p.col_l[(size_t)band * p.n_pad + col_base + 32 + lane] = cs[1];
           if (lane == 0) p.col_c[(size_t)band * (p.n_pad / 64) + col_base / 64] = cw;
+        } else if (MODE == MODE_RANK) {
+          // ---- rank-of-label epilogue (the logit scale is positive, so ranks are taken on the raw cosines)
+          const int my_cls = row_valid ? rk_cls : -2;
+          if (p.rk_phase == 0) {
+#pragma unroll 4
+            for (int c = 0; c < 64; ++c) {
+              const int j = col_base + c;
+              if (__ldg(p.rk_col_cls + j) == my_cls) p.rk_pos[rk_off + __ldg(p.rk_col_ord + j)] = __uint_as_float(raw[c]);
+            }
+          } else {
+#pragma unroll 2
+            for (int c = 0; c < 64; ++c) {
+              const int cc = __ldg(p.rk_col_cls + col_base + c);
+              const float a = __uint_as_float(raw[c]);
+              if (cc < 0 || cc == my_cls || !row_valid) continue;       // padding, positive, dead row
+              if (a > rk_lmax) ++rk_nbest;
+              if (a > rk_lmin) {
+                int cnt = 0;
+#pragma unroll
+                for (int t = 0; t < 32; ++t) cnt += (a > rk_l[t]) ? 1 : 0;
+                rk_npairs += cnt;
+              }
+            }
+          }
         } else if (kFwd && LOSS == LOSS_CLIP) {
           float v[64];
 #pragma unroll
@@ -781,7 +839,12 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }  // tiles
 
       // ------------------------------------------------------------------ item outputs
-      if (kFwd && LOSS == LOSS_CLIP) {
+      if (MODE == MODE_RANK) {
+        if (p.rk_phase == 1 && row_valid) {
+          if (rk_npairs) atomicAdd(p.rk_pairs + grow, rk_npairs);
+          if (rk_nbest) atomicAdd(p.rk_best + grow, rk_nbest);
+        }
+      } else if (kFwd && LOSS == LOSS_CLIP) {
         const int slot = (p.chunk_base + chunk) * 2 + h;
         p.row_part[(size_t)slot * p.m_pad + grow] = make_float2(m_run, l_run);
         if (Cfg::kRowEnt) p.row_ent[(size_t)slot * p.m_pad + grow] = u_run;

@@ -15,6 +15,8 @@ loss (1e-3), feature gradients (1e-2, norm-wise), d logit_scale / d logit_bias (
     c4       SigLipLoss + logit_bias   N=16384 D=768      (configs[3])
     mpos     MultiPositiveClipLoss     N=8192  D=512      (512 label classes)
     ragged   ClipLoss (T,T)            n=1000 per rank, D=200 (no tile / vector alignment anywhere)
+    exchange neighbour_exchange*       n=512 per rank: hop results and gradients exact; the reference's "shift" SigLIP
+                                       loop (loss.py:404-421) built on them equals the gathered form (several ranks only)
 
 and each is run over NVLink peer memory (default) and over NCCL collectives (``-nccl``).  Exit code 1 on any mismatch;
 one line per case / backend with the worst error over ranks.
@@ -42,6 +44,8 @@ CASES = {
     "c2raw": dict(kind="clip", N=4096, D=512, scale=2.659, modes=[(True, True), (False, True)], raw=True),
     "c4raw": dict(kind="siglip", N=4096, D=768, scale=2.3026, bias=-10.0, raw=True),
     "mpos": dict(kind="mpos", N=8192, D=512, scale=14.285714, classes=512, delta=0.3),
+    # the ring hops (neighbour_exchange*, loss.py:226-311) on NCCL + the reference's "shift" SigLIP built on them
+    "exchange": dict(kind="exchange", n=512, D=256, scale=10.0, bias=-10.0),
     "ragged": dict(kind="clip", n=1000, D=200, scale=30.0, modes=[(True, True), (False, True)], corr=0.2),
 }
 
@@ -51,6 +55,60 @@ def features(N, D, seed, device, corr=0.5):
     img = torch.nn.functional.normalize(torch.randn(N, D, generator=g), dim=-1)
     txt = torch.nn.functional.normalize(corr * img + (1.0 - corr) * torch.randn(N, D, generator=g) / D ** 0.5, dim=-1)
     return img.bfloat16().to(device), txt.bfloat16().to(device)
+
+
+def exchange_case(c, rank, world, dev):
+    """The ring hops on the real process group: values and gradients are exact; the "shift" SigLIP loop of the reference
+    (loss.py:404-421) written with them gives the loss / gradients of the gathered form (torch_ref.siglip_reference)."""
+    import torch.nn.functional as F
+    from mrclip_b200 import (neighbour_exchange, neighbour_exchange_bidir, neighbour_exchange_bidir_with_grad,
+                             neighbour_exchange_with_grad)
+    left, right = (rank - 1) % world, (rank + 1) % world
+    bad = []
+    x = torch.full((4, 8), float(rank), device=dev)
+    if not torch.equal(neighbour_exchange(left, right, x), torch.full_like(x, float(left))):
+        bad.append("neighbour_exchange")
+    # (two ranks: left == right and the reference never calls the two-sided hop -- (W - 1) // 2 == 0, loss.py:372)
+    fr, fl = neighbour_exchange_bidir(left, right, x + 0.25, x + 0.5) if world > 2 else (x + 0.25 - rank + right, x + 0.5 - rank + left)
+    if not (torch.equal(fr, torch.full_like(x, right + 0.25)) and torch.equal(fl, torch.full_like(x, left + 0.5))):
+        bad.append("neighbour_exchange_bidir")
+    a = x.clone().requires_grad_(True)
+    (neighbour_exchange_with_grad(left, right, a) * (rank + 1)).sum().backward()
+    if not torch.equal(a.grad, torch.full_like(x, float(right + 1))):       # my rows were weighted by the rank to my right
+        bad.append("neighbour_exchange_with_grad")
+    if world > 2:
+        a, b = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+        fr, fl = neighbour_exchange_bidir_with_grad(left, right, a, b)
+        (fr * (rank + 1) + fl * 10 * (rank + 1)).sum().backward()
+        # a went left: the left rank received it as its "from right" (weight left+1); b went right: weight 10*(right+1)
+        if not (torch.equal(a.grad, torch.full_like(x, float(left + 1))) and torch.equal(b.grad, torch.full_like(x, 10.0 * (right + 1)))):
+            bad.append("neighbour_exchange_bidir_with_grad")
+    # the reference's shift loop on top of the hops
+    n, D = c["n"], c["D"]
+    img, txt = features(n * world, D, 4321, dev)
+    rows = slice(rank * n, (rank + 1) * n)
+    i = img[rows].float().clone().requires_grad_(True)
+    t = txt[rows].float().clone().requires_grad_(True)
+    s = torch.tensor(c["scale"], device=dev, requires_grad=True)
+    bz = torch.tensor(c["bias"], device=dev, requires_grad=True)
+
+    def chunk_loss(tf, negative_only):
+        logits = s * i @ tf.T + bz
+        labels = -torch.ones_like(logits)
+        if not negative_only:
+            labels = labels + 2 * torch.eye(n, device=dev)
+        return -F.logsigmoid(labels * logits).sum() / n
+    loss = chunk_loss(t, False)
+    to_right = t
+    for _ in range(world - 1):
+        from_left = neighbour_exchange_with_grad(left, right, to_right)
+        loss = loss + chunk_loss(from_left, True)
+        to_right = from_left
+    loss.backward()
+    ref = torch_ref.siglip_reference(img[rows], txt[rows], c["scale"], c["bias"], rank, world)
+    errs, bad2 = torch_ref.compare(dict(loss=loss.detach(), d_image=i.grad, d_text=t.grad, d_scale=s.grad, d_bias=bz.grad), ref,
+                                   tol_loss=1e-5, tol_grad=1e-4)
+    return bad + bad2, errs
 
 
 def main():
@@ -68,6 +126,19 @@ def main():
     failures = 0
     for name in names:
         c = CASES[name]
+        if c["kind"] == "exchange":
+            if world == 1:
+                continue
+            bad, errs = exchange_case(c, rank, world, dev)
+            flag = torch.tensor([float(len(bad))], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+            failures += int(flag.item() > 0)
+            if bad:
+                print(f"MISMATCH rank {rank} exchange: {bad} {errs}", flush=True)
+            if rank == 0:
+                print(f"exchange W={world}: ring hops exact, shift-SigLIP on the hops vs gathered form: " +
+                      " ".join(f"{k}={v:.2e}" for k, v in errs.items()) + f"  [{'ok' if flag.item() == 0 else 'FAIL'}]", flush=True)
+            continue
         N = c["N"] if "N" in c else c["n"] * world
         if N % world:
             continue

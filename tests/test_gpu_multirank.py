@@ -48,4 +48,4 @@ def test_production_size_parity_multi_gpu(world):
     scaling numbers are quoted on (c3: N=32768, D=768; c2: N=4096, D=512; c4: SigLIP N=16384)."""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs, have {torch.cuda.device_count()}")
-    _run_parity(world, ["c3", "c2", "c2s100", "c2raw", "c4", "c4raw", "mpos", "ragged"])
+    _run_parity(world, ["c3", "c2", "c2s100", "c2raw", "c4", "c4raw", "mpos", "ragged", "exchange"])
