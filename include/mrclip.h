@@ -282,6 +282,24 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
                          int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
                          float* d_bias, void* stream);
 
+/* ---- retrieval metrics (reference open_clip_train/train.py:465-534, get_clip_metrics) ---------------------------------
+ * The reference forms the full logit matrix on the CPU, argsorts every row and walks Python loops to find where the
+ * samples of the row's class ("positives") rank.  Here the same S = A . B^T tiles carry a rank-of-label epilogue:
+ *   mrclip_rank_collect: pos[row_off[i] + col_ord[j]] = <A_i, B_j> for every column j of row i's class
+ *   mrclip_rank_lmax:    lmax[i] = largest positive of row i
+ *   mrclip_rank_count:   best[i] += #{k negative: C_ik > lmax[i]}   (chunk0 == 0 only; the best positive's 0-based rank)
+ *                        pairs[i] += #{(k negative, t in [chunk0, chunk0 + 32) positive): C_ik > pos_i[t]}
+ * so that  min rank = best,  mean rank of the positives = (pairs + m (m - 1) / 2) / m  (m = class size), with strict
+ * comparisons (a negative that ties a positive ranks after it).  a_rows / b_all: packed bf16 [*, ld]; row_cls [m_rows],
+ * row_off [m_rows] (int64), row_m [m_rows]; col_cls / col_ord [mrclip_padded_cols(n_cols)] with class -1 in the padding;
+ * pairs: uint64 [m_rows], best: int32 [m_rows], both zeroed by the caller.  shape.label_offset is ignored. */
+int mrclip_rank_collect(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const int* row_cls,
+                        const int* col_cls, const int* col_ord, const long long* row_off, float* pos, void* stream);
+int mrclip_rank_lmax(const float* pos, const long long* row_off, const int* row_m, int rows, float* lmax, void* stream);
+int mrclip_rank_count(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const int* row_cls,
+                      const int* col_cls, const long long* row_off, const int* row_m, const float* pos, const float* lmax,
+                      int chunk0, unsigned long long* pairs, int* best, void* stream);
+
 /* Optional timing of the launch groups inside the whole-step entries (bench.py's roofline): while enabled, CUDA events
  * are recorded on the launching stream around each group; mrclip_prof_report synchronises them and writes
  * "name:total_ms:count;..." into buf.  mrclip_prof_enable(0/1) also discards what was recorded.  Off by default. */

@@ -65,6 +65,9 @@ SIGNATURES = {
     "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _I, _P, _P]),
     "mrclip_normalize_bwd": (_I, [_P, _L, _P, _I, _I, _P, _I, _L, _P]),
     "mrclip_step_backward": (_I, [_P, _P, _P, _F, _P, _I, _L, _P, _I, _L, _P, _P, _P]),
+    "mrclip_rank_collect": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P]),
+    "mrclip_rank_lmax": (_I, [_P, _P, _P, _I, _P, _P]),
+    "mrclip_rank_count": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),
     "mrclip_prof_enable": (_I, [_I]),
     "mrclip_prof_report": (_I, [C.c_char_p, C.c_size_t]),
     "mrclip_launch_count": (_L, []),

@@ -626,6 +626,20 @@ __global__ void row_ent_split_kernel(const float2* __restrict__ row_part, const 
     atomicAdd(out + (size_t)(blockIdx.x & 63) * 2 * ranks + q, acc[q]);
 }
 
+// retrieval metrics: lmax[i] = largest entry of row i's positive list (one warp per row)
+__global__ void rank_lmax_kernel(const float* __restrict__ pos, const long long* __restrict__ off, const int* __restrict__ m,
+                                 int rows, float* __restrict__ lmax) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  for (long r = blockIdx.x * (long)wpb + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * wpb) {
+    const float* p = pos + off[r];
+    float v = -CUDART_INF_F;
+    for (int t = lane; t < m[r]; t += 32) v = fmaxf(v, p[t]);
+    v = warp_max(v);
+    if (lane == 0) lmax[r] = v;
+  }
+}
+
 // all-gather by peer stores: copy `bytes` (multiple of 16) from src to dst[k] + offset for every k != skip.
 // dsts are NVLink-mapped addresses of the same buffer on every rank; a warp writes 512 contiguous bytes, so the
 // link sees full 128-byte packets.  grid.y = destination.

@@ -1474,3 +1474,72 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
 }
 
 }  // extern "C"
+
+/* ---- retrieval metrics: rank-of-label epilogue on the S tiles (tile_kernel<MODE_RANK>) ---------------------------- */
+namespace {
+int run_rank(int phase, const void* a_rows, const void* b_all, const mrclip_shape& sh, int ld, const int* row_cls,
+             const int* col_cls, const int* col_ord, const long long* row_off, const int* row_m, float* pos,
+             const float* lmax, int chunk0, unsigned long long* pairs, int* best, cudaStream_t st) {
+  if (int e = check_shape(sh, ld)) return e;
+  if (!a_rows || !b_all || !row_cls || !col_cls || !row_off || !pos) return fail(-1, "rank: NULL argument");
+  const FwdPlan f = fwd_plan(sh.m_rows, sh.n_cols);
+  CUtensorMap ma, mb;
+  if (int e = make_map(&ma, a_rows, sh.m_rows, ld, ld, kBM)) return e;
+  if (int e = make_map(&mb, b_all, sh.n_cols, ld, ld, kSBN)) return e;
+  TileParams p;
+  memset(&p, 0, sizeof p);
+  p.m_rows = sh.m_rows;
+  p.n_cols = sh.n_cols;
+  p.num_kb = ceil_div(ld, kBK);
+  p.num_rb = f.num_rb;
+  p.tile_begin = 0;
+  p.tile_end = f.num_ct;
+  p.tiles_per_chunk = f.tiles_per_chunk;
+  p.num_chunks = f.total_chunks;
+  p.num_dc = 1;
+  p.num_items = f.total_chunks * f.num_rb;
+  p.m_pad = f.m_pad;
+  p.n_pad = f.n_pad;
+  p.rk_row_cls = row_cls;
+  p.rk_col_cls = col_cls;
+  p.rk_col_ord = col_ord;
+  p.rk_off = row_off;
+  p.rk_m = row_m;
+  p.rk_pos = pos;
+  p.rk_lmax = lmax;
+  p.rk_pairs = pairs;
+  p.rk_best = best;
+  p.rk_phase = phase;
+  p.rk_chunk0 = chunk0;
+  return launch_tile<MODE_RANK, LOSS_CLIP, 256, kSBN>(ma, mb, mb, p, st);
+}
+}  // namespace
+
+extern "C" {
+
+int mrclip_rank_collect(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const int* row_cls,
+                        const int* col_cls, const int* col_ord, const long long* row_off, float* pos, void* stream) {
+  if (!col_ord) return fail(-1, "rank_collect: NULL col_ord");
+  return run_rank(0, a_rows, b_all, shape, ld, row_cls, col_cls, col_ord, row_off, nullptr, pos, nullptr, 0, nullptr, nullptr,
+                  (cudaStream_t)stream);
+}
+
+int mrclip_rank_lmax(const float* pos, const long long* row_off, const int* row_m, int rows, float* lmax, void* stream) {
+  if (!pos || !row_off || !row_m || !lmax || rows <= 0) return fail(-1, "rank_lmax: bad arguments");
+  long blocks = ((long)rows + 7) / 8;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  rank_lmax_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(pos, row_off, row_m, rows, lmax);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_rank_count(const void* a_rows, const void* b_all, mrclip_shape shape, int ld, const int* row_cls,
+                      const int* col_cls, const long long* row_off, const int* row_m, const float* pos, const float* lmax,
+                      int chunk0, unsigned long long* pairs, int* best, void* stream) {
+  if (!row_m || !lmax || !pairs || !best || chunk0 < 0) return fail(-1, "rank_count: bad arguments");
+  return run_rank(1, a_rows, b_all, shape, ld, row_cls, col_cls, nullptr, row_off, row_m, const_cast<float*>(pos), lmax, chunk0,
+                  pairs, best, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -398,7 +398,7 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const uint32_t q = warp & 3;          // TMEM lane quarter this warp may touch
     const uint32_t h = (warp - 2) >> 2;   // which 64-column half of the tile
     const uint32_t row_in_tile = q * 32 + lane;
-    const float s = __ldg(p.scale);
+    const float s = (MODE == MODE_RANK) ? 1.f : __ldg(p.scale);   // (ranks are scale invariant: no scale operand there)
     const float sl = s * kLog2e;
     float bias = 0.f;
     if (LOSS == LOSS_SIGLIP && p.bias != nullptr) bias = __ldg(p.bias);
@@ -585,13 +585,13 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           // ---- rank-of-label epilogue (the logit scale is positive, so ranks are taken on the raw cosines)
           const int my_cls = row_valid ? rk_cls : -2;
           if (p.rk_phase == 0) {
-#pragma unroll 4
+#pragma unroll
             for (int c = 0; c < 64; ++c) {
               const int j = col_base + c;
               if (__ldg(p.rk_col_cls + j) == my_cls) p.rk_pos[rk_off + __ldg(p.rk_col_ord + j)] = __uint_as_float(raw[c]);
             }
           } else {
-#pragma unroll 2
+#pragma unroll
             for (int c = 0; c < 64; ++c) {
               const int cc = __ldg(p.rk_col_cls + col_base + c);
               const float a = __uint_as_float(raw[c]);
