@@ -224,7 +224,7 @@ int mrclip_siglip_e_scalars(mrclip_shape shape, void* ws, float coef, const floa
  *
  * mrclip_peer: plumbing of one workspace.  Every buffer named "_peers" is a device array [ranks] of NVLink-mapped
  * addresses of the SAME symmetric buffer on every rank (own rank included).  ctl_block: symmetric,
- * mrclip_peer_block_bytes() bytes, zeroed once; ctl: plain device memory, 64 int32, zeroed once.  ranks <= 1: all
+ * mrclip_peer_block_bytes() bytes, zeroed once; ctl: plain device memory, 128 int32, zeroed once.  ranks <= 1: all
  * pointers may be NULL. */
 typedef struct mrclip_peer {
   int ranks, rank;

@@ -1091,6 +1091,15 @@ int check_step(const mrclip_step* s) {
   return 0;
 }
 
+struct SideStream;
+SideStream* side_stream();
+int push_rows_async(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st);
+// overlap: the peer stores of the text rows run on a side stream (push_rows_kernel) while the forward starts on this
+// rank's own columns; otherwise the pack kernel itself stores to every rank.  MRCLIP_AG_OVERLAP=0 switches it off.
+bool ag_overlap() {
+  const char* e = getenv("MRCLIP_AG_OVERLAP");
+  return !(e && atoi(e) == 0);
+}
 int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img_dtype, long img_ld, const void* txt,
               int txt_dtype, long txt_ld, const float* log_scale, int raw, cudaStream_t st) {
   if (img_dtype < 0 || img_dtype > 2 || txt_dtype < 0 || txt_dtype > 2) return fail(-1, "step: bad feature dtype");
@@ -1112,22 +1121,24 @@ int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img
   pp.row0 = s->shape.label_offset;
   const int vec_ok = (img_ld % 8 == 0 && txt_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(txt) & 15) == 0) ? 1 : 0;
+  const bool overlap = pi.ranks > 1 && ag_overlap() && side_stream() != nullptr;
+  const int push_mode = (pi.ranks > 1 && !overlap) ? PACK_PUSH : PACK_LOCAL;
   if (raw) {   // un-normalised tower outputs: one warp per row
     if (!s->inv_norm || !s->scale_buf) return fail(-1, "step: raw forward needs inv_norm and scale_buf");
     long blocks = (2L * pp.rows + 7) / 8;
     if (blocks > 148L * 8) blocks = 148L * 8;
-    packnorm2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok, s->inv_norm, log_scale, s->scale_buf);
+    packnorm2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok, push_mode, s->inv_norm, log_scale, s->scale_buf);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
-    return 0;
+    return overlap ? push_rows_async(s, pi, st) : 0;
   }
   const long total = 2L * pp.rows * (pp.ld / 8);
   long blocks = (total + 255) / 256;
   if (blocks > 148L * 8) blocks = 148L * 8;
-  pack2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok);
+  pack2_push_kernel<<<(int)blocks, 256, 0, st>>>(pp, pi, vec_ok, push_mode);
   g_launches.fetch_add(1);
   CUDA_TRY(cudaGetLastError());
-  return 0;
+  return overlap ? push_rows_async(s, pi, st) : 0;
 }
 
 // Second stream + events of the banded backward (rescale pass of band b+1 overlapped with the dI GEMM of band b).
@@ -1135,7 +1146,7 @@ int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img
 constexpr int kMaxBands = 16;
 struct SideStream {
   cudaStream_t st = nullptr;
-  cudaEvent_t fork = nullptr, ev[kMaxBands] = {};
+  cudaEvent_t fork = nullptr, join = nullptr, ev[kMaxBands] = {};
 };
 SideStream* side_stream() {
   static std::mutex mu;
@@ -1147,7 +1158,8 @@ SideStream* side_stream() {
   if (it != per_dev.end()) return it->second;
   SideStream* s = new SideStream();
   bool ok = cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) == cudaSuccess &&
-            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess;
+            cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess &&
+            cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < kMaxBands; ++i) ok = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     delete s;
@@ -1165,6 +1177,33 @@ int pick_bands(int n) {
   }
   (void)n;
   return 1;   // measured on B200 (profiles/r2/r2c_*): no gain yet -- the two kernels contend for the SMs' registers
+}
+
+constexpr int kCtlDestDone = 32;   // ctl ints [32, 32 + kPeerMaxRanks): per-destination block counters of push_rows_kernel
+int push_rows_async(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st) {
+  SideStream* ss = side_stream();
+  if (!ss) return fail(-1, "step: no side stream");
+  CUDA_TRY(cudaEventRecord(ss->fork, st));
+  CUDA_TRY(cudaStreamWaitEvent(ss->st, ss->fork, 0));
+  const size_t bytes = (size_t)s->shape.m_rows * s->ld * 2, offset = (size_t)s->shape.label_offset * s->ld * 2;
+  int blocks = num_sms();                      // <= one 256-thread block per SM: the forward's CTAs fit beside it
+  if ((long)blocks * 256 > (long)(bytes / 16)) blocks = (int)((bytes / 16 + 255) / 256);
+  ProfScope ps("push_rows(side)", ss->st);
+  push_rows_kernel<<<blocks, 256, 0, ss->st>>>(
+      reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s->txt_all) + offset), (long)(bytes / 16),
+      s->peer.txt_peers, (long)offset, pi, s->peer.ctl + kCtlDestDone);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaEventRecord(ss->join, ss->st));
+  return 0;
+}
+// the forward's later kernels (and everything after them) are ordered behind the side-stream push
+int push_rows_join(const PeerInfo& pi, cudaStream_t st) {
+  if (pi.ranks > 1 && ag_overlap()) {
+    SideStream* ss = side_stream();
+    if (ss) CUDA_TRY(cudaStreamWaitEvent(st, ss->join, 0));
+  }
+  return 0;
 }
 
 int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pass's entropy sums on every shape
@@ -1253,6 +1292,7 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
                           need_grad ? s->emat : nullptr, st, false, &sig))
         return e;
     }
+    if (int e = push_rows_join(pi, st)) return e;
     ProfScope ps("fwd_reduce", st);
     scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
                                              (long)f.num_rb * f.total_chunks * kEpiWarps, 1.f / (float)n, 0.f, nullptr,
@@ -1268,6 +1308,7 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
                         need_grad ? s->emat : nullptr, st, fwd_ds, &sig))
       return e;
   }
+  if (int e = push_rows_join(pi, st)) return e;
   ProfScope ps("fwd_reduce", st);
   const float2* row_part = reinterpret_cast<const float2*>(wsb + w.row_part);
   const long plane = (long)rank * 3 * N;

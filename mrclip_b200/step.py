@@ -51,7 +51,7 @@ class StepPlan:
         self.ws, self.kind, self.rank = ws, kind, rank
         dev = ws.img_all.device
         self.small = torch.zeros(int(self.lib.mrclip_step_small_floats()), dtype=torch.float32, device=dev)
-        self.ctl = torch.zeros(64, dtype=torch.int32, device=dev)
+        self.ctl = torch.zeros(128, dtype=torch.int32, device=dev)
         self.inv_norm = torch.zeros((2, ws.n), dtype=torch.float32, device=dev)      # raw forward: 1/||x|| of every row
         self.scale_buf = torch.zeros((1,), dtype=torch.float32, device=dev)          # raw forward: exp(log-scale)
         rows = slice(rank * ws.n, (rank + 1) * ws.n)
