@@ -236,6 +236,13 @@ typedef struct mrclip_peer {
   const unsigned long long* recv_peers;   /* [ranks][n][d] receive slots of the fused reduce-scatter (fp32 or bf16) */
   void* recv;                             /* this rank's receive slots */
   int recv_bf16;
+  /* HOST copies of ctl_block_peers / txt_peers and a host counter (one int, zero-initialised, owned by the caller): the
+   * text all-gather runs on the copy engines (cudaMemcpyAsync to the peers' buffers on a side stream, each followed by
+   * a stream memory operation that raises the destination's flag), so the forward kernel keeps every SM.  NULL: the
+   * pack kernel stores the rows to the peers itself before the forward starts (no overlap). */
+  const unsigned long long* ctl_block_peers_host;
+  const unsigned long long* txt_peers_host;
+  int* host_epoch;
 } mrclip_peer;
 
 typedef struct mrclip_step {

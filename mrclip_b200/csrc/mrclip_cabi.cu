@@ -1094,6 +1094,7 @@ int check_step(const mrclip_step* s) {
 struct SideStream;
 SideStream* side_stream();
 int push_rows_async(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st);
+bool step_overlaps(const mrclip_step* s, const PeerInfo& pi);
 // overlap: the peer stores of the text rows run on a side stream (push_rows_kernel) while the forward starts on this
 // rank's own columns; otherwise the pack kernel itself stores to every rank.  MRCLIP_AG_OVERLAP=0 switches it off.
 bool ag_overlap() {
@@ -1102,6 +1103,7 @@ bool ag_overlap() {
 }
 int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img_dtype, long img_ld, const void* txt,
               int txt_dtype, long txt_ld, const float* log_scale, int raw, cudaStream_t st) {
+  if (pi.ranks > 1 && s->peer.host_epoch) *s->peer.host_epoch += 1;     // host twin of the CH_TEXT epoch
   if (img_dtype < 0 || img_dtype > 2 || txt_dtype < 0 || txt_dtype > 2) return fail(-1, "step: bad feature dtype");
   if (img_ld < s->shape.d || txt_ld < s->shape.d) return fail(-1, "step: feature leading dimension < d");
   Pack2Params pp;
@@ -1121,7 +1123,7 @@ int step_pack(const mrclip_step* s, const PeerInfo& pi, const void* img, int img
   pp.row0 = s->shape.label_offset;
   const int vec_ok = (img_ld % 8 == 0 && txt_ld % 8 == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
                       (reinterpret_cast<uintptr_t>(txt) & 15) == 0) ? 1 : 0;
-  const bool overlap = pi.ranks > 1 && ag_overlap() && side_stream() != nullptr;
+  const bool overlap = step_overlaps(s, pi);
   const int push_mode = (pi.ranks > 1 && !overlap) ? PACK_PUSH : PACK_LOCAL;
   if (raw) {   // un-normalised tower outputs: one warp per row
     if (!s->inv_norm || !s->scale_buf) return fail(-1, "step: raw forward needs inv_norm and scale_buf");
@@ -1179,31 +1181,57 @@ int pick_bands(int n) {
   return 1;   // measured on B200 (profiles/r2/r2c_*): no gain yet -- the two kernels contend for the SMs' registers
 }
 
-constexpr int kCtlDestDone = 32;   // ctl ints [32, 32 + kPeerMaxRanks): per-destination block counters of push_rows_kernel
+// cuStreamWriteValue32: a 32-bit store in stream order, executed by the front end -- no SM, no kernel
+typedef CUresult (*WriteValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+WriteValue32Fn write_value32_fn() {
+  static WriteValue32Fn fn = nullptr;
+  static bool tried = false;
+  if (tried) return fn;
+  tried = true;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+    fn = reinterpret_cast<WriteValue32Fn>(p);
+  return fn;
+}
+// The all-gather proper, on the copy engines: this rank's packed text rows go to the same place of every other rank's
+// buffer, destination by destination in the order in which the destinations will need them (rank r works through the
+// sources r, r+1, r+2, ... so source q serves q-1 first, then q-2, ...), each copy followed by a stream memory
+// operation that raises that destination's CH_TEXT flag.  The forward kernel, which fills every SM's shared memory,
+// meanwhile runs on this rank's own columns.
 int push_rows_async(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st) {
   SideStream* ss = side_stream();
-  if (!ss) return fail(-1, "step: no side stream");
+  WriteValue32Fn wv = write_value32_fn();
+  if (!ss || !wv) return fail(-1, "step: no side stream / stream memory operations");
   CUDA_TRY(cudaEventRecord(ss->fork, st));
   CUDA_TRY(cudaStreamWaitEvent(ss->st, ss->fork, 0));
   const size_t bytes = (size_t)s->shape.m_rows * s->ld * 2, offset = (size_t)s->shape.label_offset * s->ld * 2;
-  int blocks = num_sms();                      // <= one 256-thread block per SM: the forward's CTAs fit beside it
-  if ((long)blocks * 256 > (long)(bytes / 16)) blocks = (int)((bytes / 16 + 255) / 256);
-  ProfScope ps("push_rows(side)", ss->st);
-  push_rows_kernel<<<blocks, 256, 0, ss->st>>>(
-      reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(s->txt_all) + offset), (long)(bytes / 16),
-      s->peer.txt_peers, (long)offset, pi, s->peer.ctl + kCtlDestDone);
-  g_launches.fetch_add(1);
-  CUDA_TRY(cudaGetLastError());
+  const int e = *s->peer.host_epoch;          // already advanced for this step (mrclip_step_forward)
+  ProfScope ps("push_rows(copy engines)", ss->st);
+  for (int k = 1; k < pi.ranks; ++k) {
+    const int dest = (pi.rank - k + pi.ranks) % pi.ranks;
+    CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<void*>(s->peer.txt_peers_host[dest] + offset),
+                             reinterpret_cast<const uint8_t*>(s->txt_all) + offset, bytes, cudaMemcpyDeviceToDevice, ss->st));
+    const CUresult r = wv((CUstream)ss->st,
+                          (CUdeviceptr)(s->peer.ctl_block_peers_host[dest] + (size_t)(CH_TEXT * kPeerMaxRanks + pi.rank) * 4),
+                          (cuuint32_t)e, 0);
+    if (r != CUDA_SUCCESS) return fail(-4, "cuStreamWriteValue32 failed with CUresult %d", (int)r);
+  }
   CUDA_TRY(cudaEventRecord(ss->join, ss->st));
   return 0;
 }
 // the forward's later kernels (and everything after them) are ordered behind the side-stream push
-int push_rows_join(const PeerInfo& pi, cudaStream_t st) {
-  if (pi.ranks > 1 && ag_overlap()) {
+int push_rows_join(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st) {
+  if (step_overlaps(s, pi)) {
     SideStream* ss = side_stream();
     if (ss) CUDA_TRY(cudaStreamWaitEvent(st, ss->join, 0));
   }
   return 0;
+}
+
+bool step_overlaps(const mrclip_step* s, const PeerInfo& pi) {
+  return pi.ranks > 1 && ag_overlap() && s->peer.txt_peers_host && s->peer.ctl_block_peers_host && s->peer.host_epoch &&
+         side_stream() != nullptr && write_value32_fn() != nullptr;
 }
 
 int ds_env_entropy() {   // MRCLIP_DS=entropy: d logit_scale from the rescale pass's entropy sums on every shape
@@ -1292,7 +1320,7 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
                           need_grad ? s->emat : nullptr, st, false, &sig))
         return e;
     }
-    if (int e = push_rows_join(pi, st)) return e;
+    if (int e = push_rows_join(s, pi, st)) return e;
     ProfScope ps("fwd_reduce", st);
     scalar_reduce_kernel<<<1, 1024, 0, st>>>(reinterpret_cast<const float2*>(wsb + w.sc_part),
                                              (long)f.num_rb * f.total_chunks * kEpiWarps, 1.f / (float)n, 0.f, nullptr,
@@ -1308,7 +1336,7 @@ int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, lo
                         need_grad ? s->emat : nullptr, st, fwd_ds, &sig))
       return e;
   }
-  if (int e = push_rows_join(pi, st)) return e;
+  if (int e = push_rows_join(s, pi, st)) return e;
   ProfScope ps("fwd_reduce", st);
   const float2* row_part = reinterpret_cast<const float2*>(wsb + w.row_part);
   const long plane = (long)rank * 3 * N;

@@ -40,8 +40,9 @@ __device__ __forceinline__ uint4 load_pack8(const void* src, int dtype, long off
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-// push_mode: 0 = write this rank's buffers only (one rank, or the rows are pushed by push_rows_kernel on a side stream:
-// then the CH_TEXT epoch is advanced here, before either consumer starts); 1 = store to every rank and raise CH_TEXT.
+// push_mode: 0 = write this rank's buffers only (one rank, or the rows travel on the copy engines, mrclip_cabi.cu
+// push_rows_async: then the CH_TEXT epoch is advanced here, before either consumer starts); 1 = store to every rank and
+// raise CH_TEXT.
 enum : int { PACK_LOCAL = 0, PACK_PUSH = 1 };
 __device__ __forceinline__ void pack_bump_epoch(const PeerInfo& pi, int push_mode) {
   if (push_mode == PACK_LOCAL && pi.ranks > 1 && blockIdx.x == 0 && threadIdx.x == 0) pi.ctl->epoch[CH_TEXT] += 1;
@@ -74,32 +75,6 @@ pack2_push_kernel(const Pack2Params p, const PeerInfo pi, int vec_ok, int push_m
     }
   }
   if (pi.ranks > 1 && push_mode == PACK_PUSH) peer_signal_when_grid_done(pi, CH_TEXT, gridDim.x);
-}
-
-// The all-gather proper, on a side stream while the forward already runs on this rank's own columns: this rank's packed
-// text rows (a contiguous block of its gathered buffer) are stored into the same place of every other rank's buffer,
-// destination by destination in the order in which the destinations will need them -- rank r works through the sources
-// r, r+1, r+2, ... so source q serves q-1 first, then q-2, ... -- and each destination's CH_TEXT flag is raised the
-// moment its copy is complete.  At most one small block per SM, so that the forward's CTAs always find room beside it.
-__global__ void __launch_bounds__(256)
-push_rows_kernel(const uint4* __restrict__ src, long n16, const unsigned long long* __restrict__ txt_peers, long offset_bytes,
-                 const PeerInfo pi, int* __restrict__ dest_done) {
-  const int e = ld_relaxed_gpu(&pi.ctl->epoch[CH_TEXT]);      // advanced by the pack kernel, earlier in stream order
-  for (int k = 1; k < pi.ranks; ++k) {
-    const int dest = (pi.rank - k + pi.ranks) % pi.ranks;
-    uint4* dst = reinterpret_cast<uint4*>(__ldg(txt_peers + dest) + offset_bytes);
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n16; i += (long)gridDim.x * blockDim.x) dst[i] = src[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int prev = atomicAdd(dest_done + dest, 1);
-      if (prev == (int)gridDim.x - 1) {
-        dest_done[dest] = 0;
-        __threadfence_system();
-        st_release_sys(reinterpret_cast<int*>(__ldg(pi.sig_peers + dest)) + CH_TEXT * kPeerMaxRanks + pi.rank, e);
-      }
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -389,6 +389,11 @@ def _scalar_f32(x, device):
     return torch.tensor([float(x)], dtype=torch.float32, device=device)
 
 
+@functools.lru_cache(maxsize=None)
+def _capability(device):
+    return torch.cuda.get_device_capability(device)
+
+
 def _check_inputs(image_features, text_features):
     if not (torch.is_tensor(image_features) and torch.is_tensor(text_features)):
         raise TypeError("image_features and text_features must be tensors")
@@ -406,9 +411,9 @@ def _check_inputs(image_features, text_features):
                                f"{image_features.device} / {text_features.device}")
         if image_features.device != text_features.device:
             raise RuntimeError(f"features on different devices: {image_features.device} vs {text_features.device}")
-        if torch.cuda.get_device_capability(image_features.device)[0] != 10:
+        if _capability(image_features.device)[0] != 10:
             raise RuntimeError(f"mrclip_b200 kernels are built for sm_100a only; {image_features.device} is "
-                               f"sm_{''.join(map(str, torch.cuda.get_device_capability(image_features.device)))}")
+                               f"sm_{''.join(map(str, _capability(image_features.device)))}")
 
 
 def _scoped(fn):
@@ -428,7 +433,9 @@ class _on_device:
     current device) and the raw pointers belong to the same device.  No-op for the CPU stand-in engine of the tests."""
 
     def __init__(self, device):
-        self.guard = torch.cuda.device(device) if torch.device(device).type == "cuda" else None
+        device = torch.device(device)
+        need = device.type == "cuda" and device.index is not None and device.index != torch.cuda.current_device()
+        self.guard = torch.cuda.device(device) if need else None
 
     def __enter__(self):
         if self.guard is not None:
@@ -569,7 +576,6 @@ class _ClipLossFn(torch.autograd.Function):
     @_scoped
     def forward(ctx, image_features, text_features, logit_scale, module, raw=False):
         eng = _engine()
-        _check_inputs(image_features, text_features)
         device = image_features.device
         n, d = image_features.shape
         world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
@@ -652,7 +658,7 @@ class _ClipLossFn(torch.autograd.Function):
 
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         d_img = d_txt = d_scale = None
-        ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
+        ds = torch.zeros((1,), dtype=torch.float32, device=device) if (need_s and ctx.fast is None) else None
         # d logit_scale always uses 1/(2n) per rank; global modes average it over ranks below
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
@@ -838,7 +844,6 @@ class _MultiPositiveFn(torch.autograd.Function):
     @_scoped
     def forward(ctx, image_features, text_features, logit_scale, labels, delta, module):
         eng = _engine()
-        _check_inputs(image_features, text_features)
         device = image_features.device
         n, d = image_features.shape
         world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
@@ -974,7 +979,6 @@ class _SigLipLossFn(torch.autograd.Function):
     @_scoped
     def forward(ctx, image_features, text_features, logit_scale, logit_bias, module, raw=False):
         eng = _engine()
-        _check_inputs(image_features, text_features)
         device = image_features.device
         n, d = image_features.shape
         world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
@@ -1036,8 +1040,9 @@ class _SigLipLossFn(torch.autograd.Function):
         need_i, need_t, need_s = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         need_b = ctx.needs_input_grad[3] and ctx.bias_meta is not None
         d_img = d_txt = d_scale = d_bias = None
-        ds = torch.zeros((1,), dtype=torch.float32, device=device) if need_s else None
-        db = torch.zeros((1,), dtype=torch.float32, device=device) if need_b else None
+        mk = torch.empty if ctx.fast is not None else torch.zeros      # (the step entry overwrites, the legacy kernels add)
+        ds = mk((1,), dtype=torch.float32, device=device) if need_s else None
+        db = mk((1,), dtype=torch.float32, device=device) if need_b else None
         d_img = torch.empty((n, d), dtype=ctx.in_dtypes[0], device=device)
         d_txt = torch.empty((n, d), dtype=ctx.in_dtypes[1], device=device)
         # every rank's loss touches T_r: the column block gives the summed (W x) text gradient directly

@@ -23,7 +23,8 @@ class Peer(C.Structure):
     """``mrclip_peer`` (include/mrclip.h)."""
     _fields_ = [("ranks", C.c_int), ("rank", C.c_int), ("ctl_block_peers", C.c_void_p), ("ctl_block", C.c_void_p),
                 ("ctl", C.c_void_p), ("txt_peers", C.c_void_p), ("stats_peers", C.c_void_p), ("recv_peers", C.c_void_p),
-                ("recv", C.c_void_p), ("recv_bf16", C.c_int)]
+                ("recv", C.c_void_p), ("recv_bf16", C.c_int), ("ctl_block_peers_host", C.c_void_p),
+                ("txt_peers_host", C.c_void_p), ("host_epoch", C.c_void_p)]
 
 
 class Step(C.Structure):
@@ -55,6 +56,8 @@ class StepPlan:
         self.inv_norm = torch.zeros((2, ws.n), dtype=torch.float32, device=dev)      # raw forward: 1/||x|| of every row
         self.scale_buf = torch.zeros((1,), dtype=torch.float32, device=dev)          # raw forward: exp(log-scale)
         rows = slice(rank * ws.n, (rank + 1) * ws.n)
+        self.host_epoch = C.c_int(0)          # steps issued on this plan's flags (host twin of the device epoch)
+        self.host_ptrs = []                   # host copies of the peer address tables (kept alive here)
         self.steps = []
         for flip in ((0, 1) if ws.world > 1 else (0,)):
             st = Step()
@@ -71,11 +74,15 @@ class StepPlan:
                 stats, _, stats_ptrs = ws.sym["stats"]
                 blk, _, blk_ptrs = ws.sym["ctl"]
                 st.txt_all, st.stats = txt.data_ptr(), stats.data_ptr()
+                blk_h = (C.c_ulonglong * ws.world)(*[int(p) for p in blk_ptrs.tolist()])
+                txt_h = (C.c_ulonglong * ws.world)(*[int(p) for p in txt_ptrs.tolist()])
+                self.host_ptrs += [blk_h, txt_h]
                 st.peer = Peer(ws.world, rank, blk_ptrs.data_ptr(), blk.data_ptr(), self.ctl.data_ptr(), txt_ptrs.data_ptr(),
-                               stats_ptrs.data_ptr(), None, None, 0)
+                               stats_ptrs.data_ptr(), None, None, 0, C.addressof(blk_h), C.addressof(txt_h),
+                               C.addressof(self.host_epoch))
             else:
                 st.txt_all, st.stats = ws.txt_all.data_ptr(), ws.stats_local.data_ptr()
-                st.peer = Peer(1, 0, None, None, self.ctl.data_ptr(), None, None, None, None, 0)
+                st.peer = Peer(1, 0, None, None, self.ctl.data_ptr(), None, None, None, None, 0, None, None, None)
             self.steps.append(st)
         self.uses_fwd_ds = bool(self.lib.mrclip_step_uses_fwd_ds(C.byref(self.steps[0])))
 

@@ -79,7 +79,7 @@ def test_gpu_metrics_match_reference_function(path):
     first = voc["image_to_text_general"][0]
     assert first["anchor"] == 0 and first["gt"] == gen[0] and len(first["indices"]) == min(10, len(gen))
     s0 = img[0].astype(np.float64) @ txt.astype(np.float64).T
-    assert first["indices"][0] == int(np.argmax(s0))
+    assert abs(s0[first["indices"][0]] - s0.max()) <= 1e-6           # (duplicate captions tie exactly)
 
 
 @pytest.mark.gpu
