@@ -626,6 +626,26 @@ __global__ void row_ent_split_kernel(const float2* __restrict__ row_part, const 
     atomicAdd(out + (size_t)(blockIdx.x & 63) * 2 * ranks + q, acc[q]);
 }
 
+// dot_out += <out, feat> / scale over an [rows, d] block (out: any float dtype, feat: packed bf16); one warp per row.
+// With out = dA and feat = A this is d(loss)/d(logit_scale), by homogeneity of S = scale * A.B^T.
+__global__ void rowdot_kernel(const void* __restrict__ out, int out_dtype, long out_ld, const __nv_bfloat16* __restrict__ feat,
+                              long feat_ld, int rows, int d, const float* __restrict__ scale, float* __restrict__ dot_out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  float acc = 0.f;
+  for (long r = blockIdx.x * (long)wpb + (threadIdx.x >> 5); r < rows; r += (long)gridDim.x * wpb)
+    for (int c = lane; c < d; c += 32)
+      acc = fmaf(load_as_float(out, out_dtype, (size_t)(r * out_ld + c)), __bfloat162float(feat[r * feat_ld + c]), acc);
+  acc = warp_sum(acc);
+  __shared__ float red[32];
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < wpb) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) atomicAdd(dot_out, t / scale[0]);
+  }
+}
+
 // retrieval metrics: lmax[i] = largest entry of row i's positive list (one warp per row)
 __global__ void rank_lmax_kernel(const float* __restrict__ pos, const long long* __restrict__ off, const int* __restrict__ m,
                                  int rows, float* __restrict__ lmax) {

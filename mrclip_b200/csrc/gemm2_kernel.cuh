@@ -31,10 +31,20 @@ template <int PUSH> struct G2Cfg {
 };
 
 // GemmParams::num_rb counts 256-row pair blocks here.
-template <bool A_MN, int PUSH>
+//
+// SK (stream-K, local-output GEMMs): instead of whole (tile, K-split) items, the num_rb*num_dt*num_kb (tile, K block)
+// units form one list cut into equal contiguous ranges, one per CTA pair (GemmParams::sk_*).  A range that starts
+// inside a tile yields a CONTRIBUTOR segment, processed first: the raw fp32 accumulator goes to sk_part[pair] and
+// sk_flags[tile] is bumped (release).  A range that ends inside a tile yields the tile's OWNER segment, processed
+// last: the epilogue waits (acquire) until every contributor of the tile has arrived -- they did so long ago -- adds
+// their partials and stores the scaled result.  Whole tiles inside a range need nothing.  All pairs are resident at
+// once (grid <= SM pairs), contributors never wait, so the scheme cannot deadlock; it replaces the split-K partials
+// of whole matrices, the reduce pass over them and the wave quantisation of the item scheme.
+template <bool A_MN, int PUSH, bool SK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
              const GemmParams p) {
+  static_assert(!(SK && PUSH != 0), "stream-K serves the local-output GEMMs");
   constexpr int STAGES = G2Cfg<PUSH>::kStages;
   // M = 256 across the pair; bit 15 = A is MN-major, bit 16 = B is MN-major
   constexpr uint32_t IDESC = make_idesc_bf16(2 * kBM, kGemmBN) | (A_MN ? (1u << 15) : 0u) | (1u << 16);
@@ -92,12 +102,38 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     kb1 = min(kb0 + p.kb_per_split, p.num_kb);
   };
 
+  // stream-K: this pair's contiguous range of (tile, K block) units; a segment = the part of one tile inside it
+  const long long sk_total = (long long)p.num_rb * p.num_dt * p.num_kb;
+  const long long sk_u0 = SK ? (long long)pair * sk_total / num_pairs : 0;
+  const long long sk_u1 = SK ? (long long)(pair + 1) * sk_total / num_pairs : 0;
+  auto next_segment = [&](long long& u, int& rb, int& dt, int& kb0, int& kb1, int& tile) {
+    tile = (int)(u / p.num_kb);
+    kb0 = (int)(u - (long long)tile * p.num_kb);
+    const long long left = sk_u1 - u;
+    kb1 = (left < (long long)(p.num_kb - kb0)) ? kb0 + (int)left : p.num_kb;
+    rb = tile / p.num_dt;
+    dt = tile - rb * p.num_dt;
+    u += kb1 - kb0;
+  };
+  // one loop header for both schemes: declares rb, dt, ks, kb0, kb1, tile for the body that follows
+#define MRCLIP_G2_FOR_ITEMS                                                                              \
+  for (long long it_ = SK ? sk_u0 : (long long)pair; SK ? (it_ < sk_u1) : (it_ < (long long)p.num_items);)
+#define MRCLIP_G2_NEXT_ITEM                                           \
+  int rb, dt, ks = 0, kb0, kb1, tile = 0;                             \
+  if (SK) {                                                           \
+    next_segment(it_, rb, dt, kb0, kb1, tile);                        \
+  } else {                                                            \
+    decode((int)it_, rb, dt, ks, kb0, kb1);                           \
+    it_ += num_pairs;                                                 \
+  }                                                                   \
+  (void)ks;                                                           \
+  (void)tile;
+
   if (warp == 0) {
     // ===================================================================== TMA producer (both CTAs)
     uint32_t stage = 0, phase = 0;
-    for (int item = pair; item < p.num_items; item += num_pairs) {
-      int rb, dt, ks, kb0, kb1;
-      decode(item, rb, dt, ks, kb0, kb1);
+    MRCLIP_G2_FOR_ITEMS {
+      MRCLIP_G2_NEXT_ITEM
       const int row0 = rb * 2 * kBM + (int)cta * kBM;          // this CTA's 128 rows of the pair tile
       const int col0 = dt * kGemmBN + (int)cta * (kGemmBN / 2);  // this CTA's half of the B tile
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -126,9 +162,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     // ===================================================================== MMA issuer (leader CTA only)
     if (cta == 0) {
       uint32_t stage = 0, phase = 0, acc_use = 0;
-      for (int item = pair; item < p.num_items; item += num_pairs) {
-        int rb, dt, ks, kb0, kb1;
-        decode(item, rb, dt, ks, kb0, kb1);
+      MRCLIP_G2_FOR_ITEMS {
+        MRCLIP_G2_NEXT_ITEM
+        (void)rb;
+        (void)dt;
         const uint32_t buf = acc_use & 1, use = acc_use >> 1;
         mbar_wait(bar_accempty(buf), (use & 1) ^ 1);
         tc_fence_after();
@@ -163,10 +200,17 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t h = (warp - 2) >> 2;
     const uint32_t row_in_tile = q * 32 + lane;
     uint32_t acc_use = 0;
-    for (int item = pair; item < p.num_items; item += num_pairs) {
-      int rb, dt, ks, kb0, kb1;
-      decode(item, rb, dt, ks, kb0, kb1);
+    MRCLIP_G2_FOR_ITEMS {
+      MRCLIP_G2_NEXT_ITEM
       const uint32_t buf = acc_use & 1, use = acc_use >> 1;
+      // stream-K roles of this segment
+      const bool sk_contrib = SK && kb0 > 0;
+      const bool sk_owner = SK && kb0 == 0 && kb1 < p.num_kb;
+      int sk_others = 0;                 // owner: how many later pairs hold a part of this tile
+      if (sk_owner) {
+        const long long tile_end = (long long)(tile + 1) * p.num_kb;
+        for (int j = pair + 1; j < num_pairs && (long long)j * sk_total / num_pairs < tile_end; ++j) ++sk_others;
+      }
       mbar_wait(bar_accfull(buf), use & 1);
       tc_fence_after();
       const int grow = rb * 2 * kBM + (int)cta * kBM + row_in_tile;
@@ -176,10 +220,47 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         mul = p.coef * __ldg(p.scale);
         if (p.grad_out != nullptr) mul *= __ldg(p.grad_out);
       }
+      if (sk_owner) {    // every contributor's partial has landed (16 epilogue warps each)
+        if (lane == 0) {
+          const int want = sk_others * 2 * kEpiWarps;
+          const long long t0 = clock64();
+          while (ld_acquire_gpu(p.sk_flags + tile) < want) {
+            if (clock64() - t0 > MRCLIP_SPIN_LIMIT_CYCLES) {
+              printf("mrclip: stream-K owner timed out (pair %d tile %d want %d have %d)\n", pair, tile, want,
+                     ld_acquire_gpu(p.sk_flags + tile));
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+      }
 #pragma unroll 1
       for (int c0 = h * 128; c0 < (int)(h + 1) * 128; c0 += (PUSH == 2 ? 64 : 32)) {
         uint32_t r[32];
         tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + buf * kGemmBN + c0, r);
+        if (SK && (sk_contrib || sk_owner)) {
+          tmem_ld_wait();
+          if (sk_contrib) {   // raw accumulator -> this pair's partial slot; nothing else to do for these columns
+            float* prow = p.sk_part + (((size_t)pair * 2 + cta) * kBM + row_in_tile) * kGemmBN + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(prow + 4 * j) =
+                  make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                              __uint_as_float(r[4 * j + 3]));
+            continue;
+          }
+          for (int o = 1; o <= sk_others; ++o) {
+            const float* prow = p.sk_part + (((size_t)(pair + o) * 2 + cta) * kBM + row_in_tile) * kGemmBN + c0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 v = __ldcg(reinterpret_cast<const float4*>(prow + 4 * j));
+              r[4 * j] = __float_as_uint(__uint_as_float(r[4 * j]) + v.x);
+              r[4 * j + 1] = __float_as_uint(__uint_as_float(r[4 * j + 1]) + v.y);
+              r[4 * j + 2] = __float_as_uint(__uint_as_float(r[4 * j + 2]) + v.z);
+              r[4 * j + 3] = __float_as_uint(__uint_as_float(r[4 * j + 3]) + v.w);
+            }
+          }
+        }
         if (PUSH == 2) {
           // bf16 payload: 64 accumulator columns -> one 128-byte row piece in the owner's bf16 receive slot
           uint32_t r2[32];
@@ -271,6 +352,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           }
         }
       }
+      if (sk_contrib) {     // this warp's share of the partial is written: tell the tile's owner
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(p.sk_flags + tile, 1);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_shared(bar_accempty(buf), 0));
@@ -278,6 +364,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
     if (PUSH) bulk_wait0();   // every pushed row is complete before the kernel (and the cross-rank barrier) ends
   }
+#undef MRCLIP_G2_FOR_ITEMS
+#undef MRCLIP_G2_NEXT_ITEM
   tc_fence_before();
   if (PUSH && p.sig.ranks > 1) peer_signal_when_grid_done(p.sig, CH_DTEXT, gridDim.x);   // (contains the __syncthreads)
   __syncthreads();

@@ -49,6 +49,13 @@ struct GemmParams {
   int peer_n, peer_rank;
   // optional: raise CH_DTEXT on every rank when the last CTA's pushed rows have landed (peer_sync.cuh); sig.ranks == 0: off
   PeerInfo sig;
+  // stream-K (gemm2_kernel<.., SK>): the tiles' K blocks form one list of num_rb*num_dt*num_kb units that is cut into
+  // equal contiguous ranges, one per CTA pair.  A pair whose range starts inside a tile writes that partial accumulator
+  // to sk_part[pair] first thing and bumps sk_flags[tile]; the pair whose range ends inside a tile owns it: it
+  // accumulates the tile's first K blocks last, adds the other pairs' partials and runs the epilogue.  No split-K
+  // partials of whole matrices, no reduce pass, no wave quantisation.
+  float* sk_part;     // [pairs][2 CTAs][128 rows][256 cols] fp32
+  int* sk_flags;      // [num_rb * num_dt], zero at launch
 };
 
 // destination row of the direct epilogue: local output, or the owner's receive slot over NVLink

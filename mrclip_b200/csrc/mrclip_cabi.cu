@@ -229,6 +229,10 @@ GemmPlan gemm_plan(int out_rows, int k_len, int ld, bool force_single_split = fa
   return g;
 }
 
+// stream-K scratch at the start of the (aliased) backward view: partial tiles of up to 74 CTA pairs, then the tile flags
+constexpr int kSkMaxPairs = 74, kSkMaxTiles = 16384;
+constexpr size_t kSkPartBytes = (size_t)kSkMaxPairs * 2 * 128 * 256 * sizeof(float);
+constexpr size_t kSkBytes = kSkPartBytes + (size_t)kSkMaxTiles * sizeof(int);
 struct WsLayout {
   size_t row_part, col_l, col_c, diag2, sc_part, sc_part2, cbmin, flag, dpart, row_ent, total;
 };
@@ -254,6 +258,7 @@ WsLayout ws_layout(int m_rows, int n_cols, int d) {
     const size_t e2 = align_up((size_t)g2.ksplit * g2.m_pad * g2.d_pad * sizeof(float), 256);
     if (e1 > bwd_end) bwd_end = e1;
     if (e2 > bwd_end) bwd_end = e2;
+    if (kSkBytes > bwd_end) bwd_end = kSkBytes;      // stream-K: one partial tile per CTA pair + the tile flags
   }
   off = fwd_end > bwd_end ? fwd_end : bwd_end;
   w.sc_part = off;
@@ -444,16 +449,17 @@ int run_bwd(int loss_kind, const void* a_rows, const void* b_all, const void* bt
   return 0;
 }
 
-template <bool A_MN, int PUSH>
+template <bool A_MN, int PUSH, bool SK = false>
 int launch_gemm2(const CUtensorMap& ma, const CUtensorMap& mb, const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm2_kernel<A_MN, PUSH>;
+  auto kern = gemm2_kernel<A_MN, PUSH, SK>;
   constexpr int kG2SmemBytes = G2Cfg<PUSH>::kSmemBytes;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kG2SmemBytes));
     attr_set = true;
   }
-  const int pairs_avail = num_sms() / 2;
+  int pairs_avail = num_sms() / 2;
+  if (SK && pairs_avail > kSkMaxPairs) pairs_avail = kSkMaxPairs;
   const int pairs = p.num_items < pairs_avail ? p.num_items : pairs_avail;
   if (pairs <= 0) return 0;
   kern<<<2 * pairs, kThreads, kG2SmemBytes, st>>>(ma, mb, p);   // __cluster_dims__(2,1,1)
@@ -560,6 +566,39 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
   p.m_pad = g.m_pad;
   p.d_pad = g.d_pad;
   p.dpart = reinterpret_cast<float*>(ws);
+  // stream-K (CTA pairs, local output): no split-K partials, no reduce pass (MRCLIP_STREAMK=0: the item scheme)
+  static const bool sk_on = [] {
+    const char* e = getenv("MRCLIP_STREAMK");
+    return !(e && atoi(e) == 0);
+  }();
+  const long tiles = (long)g.num_rb * g.num_dt;
+  const bool streamk = sk_on && gemm_pairs() && xf.peer == nullptr && tiles <= kSkMaxTiles && ws != nullptr;
+  if (streamk) {
+    const long units = tiles * g.num_kb;
+    p.num_items = (int)(units < kSkMaxPairs ? units : kSkMaxPairs);      // = CTA pairs to launch
+    p.ksplit = 1;
+    p.kb_per_split = g.num_kb;
+    p.sk_part = reinterpret_cast<float*>(ws);
+    p.sk_flags = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(ws) + kSkPartBytes);
+    p.out = d_out;
+    p.out_ld = out_ld;
+    p.out_dtype = out_dtype;
+    p.d_valid = d;
+    p.coef = coef;
+    p.scale = scale;
+    p.grad_out = grad_out;
+    CUDA_TRY(cudaMemsetAsync(p.sk_flags, 0, (size_t)tiles * sizeof(int), st));
+    if (int e = transposed ? launch_gemm2<true, 0, true>(ma, mb, p, st) : launch_gemm2<false, 0, true>(ma, mb, p, st)) return e;
+    if (xf.dot_feat != nullptr) {   // <d_out, dot_feat> / scale (d logit_scale by homogeneity), formerly in the reduce pass
+      long blocks = ((long)out_rows + 7) / 8;
+      if (blocks > 148L * 8) blocks = 148L * 8;
+      rowdot_kernel<<<(int)blocks, 256, 0, st>>>(d_out, out_dtype, out_ld, reinterpret_cast<const __nv_bfloat16*>(xf.dot_feat),
+                                                 (long)ld, out_rows, d, scale, xf.dot_out);
+      g_launches.fetch_add(1);
+      CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+  }
   const bool direct = (g.ksplit == 1 && xf.dot_feat == nullptr);
   if (xf.peer && !direct) return fail(-1, "push epilogue needs a single-split GEMM");
   if (direct) {
