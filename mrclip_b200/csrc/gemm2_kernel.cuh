@@ -32,14 +32,14 @@ template <int PUSH> struct G2Cfg {
 
 // GemmParams::num_rb counts 256-row pair blocks here.
 //
-// SK (stream-K, local-output GEMMs): instead of whole (tile, K-split) items, the num_rb*num_dt*num_kb (tile, K block)
-// units form one list cut into equal contiguous ranges, one per CTA pair (GemmParams::sk_*).  A range that starts
-// inside a tile yields a CONTRIBUTOR segment, processed first: the raw fp32 accumulator goes to sk_part[pair] and
-// sk_flags[tile] is bumped (release).  A range that ends inside a tile yields the tile's OWNER segment, processed
-// last: the epilogue waits (acquire) until every contributor of the tile has arrived -- they did so long ago -- adds
-// their partials and stores the scaled result.  Whole tiles inside a range need nothing.  All pairs are resident at
-// once (grid <= SM pairs), contributors never wait, so the scheme cannot deadlock; it replaces the split-K partials
-// of whole matrices, the reduce pass over them and the wave quantisation of the item scheme.
+// SK (stream-K, local-output GEMMs): whole waves of tiles run as before (pair p: tiles p, p + P, ...); the last < P
+// tiles, which would otherwise occupy a full wave (or force split-K partials of the whole matrix and a reduce pass),
+// are cut at K-block granularity: their (tile, K block) units form one list split into equal contiguous ranges, one per
+// CTA pair (GemmParams::sk_*).  A range that starts inside a tile yields a CONTRIBUTOR segment: the raw fp32
+// accumulator goes to sk_part[pair] and sk_flags[tile] is bumped (release).  A range that ends inside a tile yields the
+// tile's OWNER segment: its epilogue waits (acquire) until every contributor of the tile has arrived, adds their
+// partials and stores the scaled result.  Within a pair the contributor segment always precedes the owner segment, and
+// contributors never wait, so the scheme cannot deadlock (all pairs are resident at once: grid <= SM pairs).
 template <bool A_MN, int PUSH, bool SK = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -102,26 +102,43 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     kb1 = min(kb0 + p.kb_per_split, p.num_kb);
   };
 
-  // stream-K: this pair's contiguous range of (tile, K block) units; a segment = the part of one tile inside it
-  const long long sk_total = (long long)p.num_rb * p.num_dt * p.num_kb;
+  // stream-K, hybrid: the first full_waves * num_pairs tiles run as whole tiles, pair p taking tiles p, p + P, ...
+  // (dt fastest, so the pairs that share a G block work on it side by side and it streams from HBM once); only the
+  // remaining < P tiles are cut into per-pair ranges of (tile, K block) units.  The ranges come FIRST, so that the
+  // owners' short wait for their contributors overlaps the MMAs of the following whole tile.
+  const int sk_tiles = p.num_rb * p.num_dt;
+  const int sk_full_waves = SK ? sk_tiles / num_pairs : 0;
+  const int sk_base_tile = sk_full_waves * num_pairs;
+  const long long sk_total = (long long)(sk_tiles - sk_base_tile) * p.num_kb;
   const long long sk_u0 = SK ? (long long)pair * sk_total / num_pairs : 0;
   const long long sk_u1 = SK ? (long long)(pair + 1) * sk_total / num_pairs : 0;
   auto next_segment = [&](long long& u, int& rb, int& dt, int& kb0, int& kb1, int& tile) {
-    tile = (int)(u / p.num_kb);
-    kb0 = (int)(u - (long long)tile * p.num_kb);
+    const int rt = (int)(u / p.num_kb);
+    tile = sk_base_tile + rt;
+    kb0 = (int)(u - (long long)rt * p.num_kb);
     const long long left = sk_u1 - u;
     kb1 = (left < (long long)(p.num_kb - kb0)) ? kb0 + (int)left : p.num_kb;
     rb = tile / p.num_dt;
     dt = tile - rb * p.num_dt;
     u += kb1 - kb0;
   };
-  // one loop header for both schemes: declares rb, dt, ks, kb0, kb1, tile for the body that follows
-#define MRCLIP_G2_FOR_ITEMS                                                                              \
-  for (long long it_ = SK ? sk_u0 : (long long)pair; SK ? (it_ < sk_u1) : (it_ < (long long)p.num_items);)
+  // one loop header for both schemes; the body starts with MRCLIP_G2_NEXT_ITEM, which declares rb, dt, ks, kb0, kb1, tile
+#define MRCLIP_G2_FOR_ITEMS                                                                                    \
+  for (long long it_ = SK ? sk_u0 : (long long)pair, fw_ = 0;                                                  \
+       SK ? (it_ < sk_u1 || fw_ < sk_full_waves) : (it_ < (long long)p.num_items);)
 #define MRCLIP_G2_NEXT_ITEM                                           \
   int rb, dt, ks = 0, kb0, kb1, tile = 0;                             \
   if (SK) {                                                           \
-    next_segment(it_, rb, dt, kb0, kb1, tile);                        \
+    if (it_ < sk_u1) {                                                \
+      next_segment(it_, rb, dt, kb0, kb1, tile);                      \
+    } else {                                                          \
+      tile = pair + (int)fw_ * num_pairs;                             \
+      rb = tile / p.num_dt;                                           \
+      dt = tile - rb * p.num_dt;                                      \
+      kb0 = 0;                                                        \
+      kb1 = p.num_kb;                                                 \
+      ++fw_;                                                          \
+    }                                                                 \
   } else {                                                            \
     decode((int)it_, rb, dt, ks, kb0, kb1);                           \
     it_ += num_pairs;                                                 \
@@ -208,7 +225,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const bool sk_owner = SK && kb0 == 0 && kb1 < p.num_kb;
       int sk_others = 0;                 // owner: how many later pairs hold a part of this tile
       if (sk_owner) {
-        const long long tile_end = (long long)(tile + 1) * p.num_kb;
+        const long long tile_end = (long long)(tile - sk_base_tile + 1) * p.num_kb;      // in remainder units
         for (int j = pair + 1; j < num_pairs && (long long)j * sk_total / num_pairs < tile_end; ++j) ++sk_others;
       }
       mbar_wait(bar_accfull(buf), use & 1);
