@@ -566,10 +566,12 @@ int run_gmat_gemm(bool transposed, const void* gmat, int g_rows, int g_cols, con
   p.m_pad = g.m_pad;
   p.d_pad = g.d_pad;
   p.dpart = reinterpret_cast<float*>(ws);
-  // stream-K (CTA pairs, local output): no split-K partials, no reduce pass (MRCLIP_STREAMK=0: the item scheme)
+  // stream-K (CTA pairs, local output): no split-K partials, no reduce pass.  Opt-in (MRCLIP_STREAMK=1): measured on B200
+  // at N=32768 it is 0.05-0.07 ms per GEMM SLOWER than split-K + reduce (profiles/r2_notes.md) -- the short split-K items
+  // keep all pairs on the same K range of the feature matrix (L2), whole-K tiles drift apart.
   static const bool sk_on = [] {
     const char* e = getenv("MRCLIP_STREAMK");
-    return !(e && atoi(e) == 0);
+    return e && atoi(e) == 1;
   }();
   const long tiles = (long)g.num_rb * g.num_dt;
   const bool streamk = sk_on && gemm_pairs() && xf.peer == nullptr && tiles <= kSkMaxTiles && ws != nullptr;
