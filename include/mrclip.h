@@ -289,6 +289,24 @@ int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* 
                          int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
                          float* d_bias, void* stream);
 
+/* ---- MultiPositiveClipLoss (reference loss.py:626-644, :671-747) on top of the ClipLoss pipeline -------------------
+ * With P(i) the samples of row i's class: loss_i = lse_i - mean_{j in P(i)} S_ij and the mean is s <I_i, mean_{P(i)} T>,
+ * so the loss needs only the row / column LSEs (the ClipLoss forward) and class means of the packed features.
+ * mrclip_class_means: mean[c] (fp32 [n_ids, ld]) = average of the rows of x (bf16 [*, ld]) of class id c; order =
+ *   sample indices grouped by class, seg_start[c] / seg_cnt[c] the group of id c (seg_cnt 0: unused id).
+ * mrclip_mpos_forward: loss[0] = (1/n) sum_i delta (lse_row_i - s <I_i, tmean[cls_i]>) + (1-delta) (lse_col_i - s <T_i, imean[cls_i]>)
+ *   over this rank's n rows (img / txt: its packed rows; lse2_*: log2 units, lse2_col indexed by local row).
+ * mrclip_mpos_backward: d_img += k (T_i - tmean[cls_i]), d_txt += k (I_i - imean[cls_i]), k = coef * scale * grad_out --
+ *   the part of the gradient that the E-block GEMMs (weights delta / 1-delta) do not carry. */
+int mrclip_class_means(const void* x, int ld, const int* order, const int* seg_start, const int* seg_cnt, int n_ids,
+                       float* mean, void* stream);
+int mrclip_mpos_forward(const void* img_rows, const void* txt_rows, int ld, int n, int d, const int* cls, const float* tmean,
+                        const float* imean, const float* lse2_row, const float* lse2_col, const float* scale, float delta,
+                        float* loss, void* stream);
+int mrclip_mpos_backward(void* d_img, int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld,
+                         const void* img_rows, const void* txt_rows, int ld, int n, int d, const int* cls, const float* tmean,
+                         const float* imean, float coef, const float* scale, const float* grad_out, void* stream);
+
 /* ---- retrieval metrics (reference open_clip_train/train.py:465-534, get_clip_metrics) ---------------------------------
  * The reference forms the full logit matrix on the CPU, argsorts every row and walks Python loops to find where the
  * samples of the row's class ("positives") rank.  Here the same S = A . B^T tiles carry a rank-of-label epilogue:

@@ -65,6 +65,9 @@ SIGNATURES = {
     "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _I, _P, _P]),
     "mrclip_normalize_bwd": (_I, [_P, _L, _P, _I, _I, _P, _I, _L, _P]),
     "mrclip_step_backward": (_I, [_P, _P, _P, _F, _P, _I, _L, _P, _I, _L, _P, _P, _P]),
+    "mrclip_class_means": (_I, [_P, _I, _P, _P, _P, _I, _P, _P]),
+    "mrclip_mpos_forward": (_I, [_P, _P, _I, _I, _I, _P, _P, _P, _P, _P, _P, _F, _P, _P]),
+    "mrclip_mpos_backward": (_I, [_P, _I, _L, _P, _I, _L, _P, _P, _I, _I, _I, _P, _P, _P, _F, _P, _P, _P]),
     "mrclip_rank_collect": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P]),
     "mrclip_rank_lmax": (_I, [_P, _P, _P, _I, _P, _P]),
     "mrclip_rank_count": (_I, [_P, _P, Shape, _I, _P, _P, _P, _P, _P, _P, _I, _P, _P, _P]),

@@ -626,6 +626,79 @@ __global__ void row_ent_split_kernel(const float2* __restrict__ row_part, const 
     atomicAdd(out + (size_t)(blockIdx.x & 63) * 2 * ranks + q, acc[q]);
 }
 
+// ---- MultiPositiveClipLoss (reference loss.py:626-644, :671-747): class statistics of the packed features -----------
+// mean[c] = average of the rows of x (bf16 [N, ld]) whose class is c.  order lists the sample indices grouped by class,
+// seg_start[c] / seg_cnt[c] delimit class c inside it (seg_cnt[c] == 0: unused id).  One block per class id, a thread
+// per pair of columns; replaces two index_add_ passes over fp32 copies of the features.
+__global__ void class_mean_kernel(const __nv_bfloat16* __restrict__ x, int ld, const int* __restrict__ order,
+                                  const int* __restrict__ seg_start, const int* __restrict__ seg_cnt, float* __restrict__ mean) {
+  const int c = blockIdx.x, cnt = seg_cnt[c];
+  if (cnt <= 0) return;
+  const int start = seg_start[c];
+  const float inv = 1.f / (float)cnt;
+  for (int c2 = threadIdx.x; c2 < ld / 2; c2 += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < cnt; ++j) {
+      const uint32_t v = *reinterpret_cast<const uint32_t*>(x + (size_t)__ldg(order + start + j) * ld + 2 * c2);
+      a0 += __uint_as_float(v << 16);
+      a1 += __uint_as_float(v & 0xffff0000u);
+    }
+    *reinterpret_cast<float2*>(mean + (size_t)c * ld + 2 * c2) = make_float2(a0 * inv, a1 * inv);
+  }
+}
+
+// loss_out[0] += (1/n) sum_i ( delta (lse_row_i - s <I_i, tmean[c_i]>) + (1 - delta) (lse_col_i - s <T_i, imean[c_i]>) ),
+// c_i = cls[i]; the mean over the positives of S_ij is s <I_i, mean_{P(i)} T> (natural-log units; lse2 are log2).
+// One warp per row.  loss_out must be zero on entry.
+__global__ void mpos_forward_kernel(const __nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ txt, int ld, int n,
+                                    int d, const int* __restrict__ cls, const float* __restrict__ tmean,
+                                    const float* __restrict__ imean, const float* __restrict__ lse2_row,
+                                    const float* __restrict__ lse2_col, const float* __restrict__ scale, float delta,
+                                    float* __restrict__ loss_out) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  const float s = scale[0];
+  float acc = 0.f;
+  for (long i = blockIdx.x * (long)wpb + (threadIdx.x >> 5); i < n; i += (long)gridDim.x * wpb) {
+    const size_t c = (size_t)cls[i] * ld;
+    float d1 = 0.f, d2 = 0.f;
+    for (int k = lane; k < d; k += 32) {
+      d1 = fmaf(__bfloat162float(img[i * ld + k]), tmean[c + k], d1);
+      d2 = fmaf(__bfloat162float(txt[i * ld + k]), imean[c + k], d2);
+    }
+    d1 = warp_sum(d1);
+    d2 = warp_sum(d2);
+    if (lane == 0)
+      acc += delta * (lse2_row[i] * 0.6931471805599453f - s * d1) + (1.f - delta) * (lse2_col[i] * 0.6931471805599453f - s * d2);
+  }
+  __shared__ float red[32];
+  if (lane == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (threadIdx.x < wpb) ? red[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0 && t != 0.f) atomicAdd(loss_out, t / (float)n);
+  }
+}
+
+// d_img[i] += k (T_i - tmean[c_i]),  d_txt[i] += k (I_i - imean[c_i]),  k = coef * scale * grad_out: the difference between
+// the multi-positive gradient of the logits and what the E-block pipeline contracts (G_k + delta_ij - [same class]/|P|).
+__global__ void mpos_backward_kernel(void* __restrict__ d_img, int di_dtype, long di_ld, void* __restrict__ d_txt, int dt_dtype,
+                                     long dt_ld, const __nv_bfloat16* __restrict__ img, const __nv_bfloat16* __restrict__ txt,
+                                     int ld, int n, int d, const int* __restrict__ cls, const float* __restrict__ tmean,
+                                     const float* __restrict__ imean, float coef, const float* __restrict__ scale,
+                                     const float* __restrict__ grad_out) {
+  const float k = coef * scale[0] * (grad_out != nullptr ? grad_out[0] : 1.f);
+  const long total = (long)n * d;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long i = e / d;
+    const int col = (int)(e - i * d);
+    const size_t c = (size_t)cls[i] * ld + col;
+    const size_t gi = (size_t)(i * di_ld + col), gt = (size_t)(i * dt_ld + col);
+    store_from_float(d_img, di_dtype, gi, load_as_float(d_img, di_dtype, gi) + k * (__bfloat162float(txt[i * ld + col]) - tmean[c]));
+    store_from_float(d_txt, dt_dtype, gt, load_as_float(d_txt, dt_dtype, gt) + k * (__bfloat162float(img[i * ld + col]) - imean[c]));
+  }
+}
+
 // dot_out += <out, feat> / scale over an [rows, d] block (out: any float dtype, feat: packed bf16); one warp per row.
 // With out = dA and feat = A this is d(loss)/d(logit_scale), by homogeneity of S = scale * A.B^T.
 __global__ void rowdot_kernel(const void* __restrict__ out, int out_dtype, long out_ld, const __nv_bfloat16* __restrict__ feat,

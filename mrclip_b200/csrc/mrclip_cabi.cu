@@ -1653,3 +1653,52 @@ int mrclip_rank_count(const void* a_rows, const void* b_all, mrclip_shape shape,
 }
 
 }  // extern "C"
+
+/* ---- MultiPositiveClipLoss: class means of the packed features and the terms built on them ----------------------- */
+extern "C" {
+
+int mrclip_class_means(const void* x, int ld, const int* order, const int* seg_start, const int* seg_cnt, int n_ids,
+                       float* mean, void* stream) {
+  if (!x || !order || !seg_start || !seg_cnt || !mean || n_ids <= 0 || ld <= 0 || ld % 8 != 0)
+    return fail(-1, "class_means: bad arguments");
+  class_mean_kernel<<<n_ids, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, order, seg_start,
+                                                            seg_cnt, mean);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_mpos_forward(const void* img_rows, const void* txt_rows, int ld, int n, int d, const int* cls, const float* tmean,
+                        const float* imean, const float* lse2_row, const float* lse2_col, const float* scale, float delta,
+                        float* loss, void* stream) {
+  if (!img_rows || !txt_rows || !cls || !tmean || !imean || !lse2_row || !lse2_col || !scale || !loss || n <= 0 || d <= 0 || ld < d)
+    return fail(-1, "mpos_forward: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(float), st));
+  long blocks = ((long)n + 7) / 8;
+  if (blocks > 148L * 8) blocks = 148L * 8;
+  mpos_forward_kernel<<<(int)blocks, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(img_rows),
+                                                   reinterpret_cast<const __nv_bfloat16*>(txt_rows), ld, n, d, cls, tmean, imean,
+                                                   lse2_row, lse2_col, scale, delta, loss);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int mrclip_mpos_backward(void* d_img, int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld,
+                         const void* img_rows, const void* txt_rows, int ld, int n, int d, const int* cls, const float* tmean,
+                         const float* imean, float coef, const float* scale, const float* grad_out, void* stream) {
+  if (!d_img || !d_txt || !img_rows || !txt_rows || !cls || !tmean || !imean || !scale || n <= 0 || d <= 0 || ld < d)
+    return fail(-1, "mpos_backward: bad arguments");
+  if (d_img_dtype < 0 || d_img_dtype > 2 || d_txt_dtype < 0 || d_txt_dtype > 2) return fail(-1, "mpos_backward: bad dtype");
+  long blocks = ((long)n * d + 255) / 256;
+  if (blocks > 148L * 16) blocks = 148L * 16;
+  mpos_backward_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(
+      d_img, d_img_dtype, d_img_ld, d_txt, d_txt_dtype, d_txt_ld, reinterpret_cast<const __nv_bfloat16*>(img_rows),
+      reinterpret_cast<const __nv_bfloat16*>(txt_rows), ld, n, d, cls, tmean, imean, coef, scale, grad_out);
+  g_launches.fetch_add(1);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

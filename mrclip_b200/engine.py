@@ -221,6 +221,27 @@ class CudaEngine:
                                                      _ptr(d_bias), int(accumulate), self._stream()))
 
 
+    # ---- MultiPositiveClipLoss: class means of the packed features and the terms built on them -------------
+    def class_means(self, x_all, order, seg_start, seg_cnt, mean_out):
+        """mean_out[c] (fp32 [N, ld]) = average of the rows of x_all (bf16 [N, ld]) of class id c."""
+        assert x_all.dtype == torch.bfloat16 and x_all.is_contiguous() and mean_out.dtype == torch.float32
+        assert order.dtype == seg_start.dtype == seg_cnt.dtype == torch.int32
+        _cabi.check(self.lib.mrclip_class_means(x_all.data_ptr(), x_all.shape[1], order.data_ptr(), seg_start.data_ptr(),
+                                                seg_cnt.data_ptr(), seg_cnt.shape[0], mean_out.data_ptr(), self._stream()))
+
+    def mpos_forward(self, img_rows, txt_rows, d, cls, tmean, imean, lse2_row, lse2_col, scale, delta, loss):
+        _cabi.check(self.lib.mrclip_mpos_forward(img_rows.data_ptr(), txt_rows.data_ptr(), img_rows.shape[1], img_rows.shape[0],
+                                                 d, cls.data_ptr(), tmean.data_ptr(), imean.data_ptr(), lse2_row.data_ptr(),
+                                                 lse2_col.data_ptr(), scale.data_ptr(), float(delta), loss.data_ptr(),
+                                                 self._stream()))
+
+    def mpos_backward(self, d_img, d_txt, img_rows, txt_rows, d, cls, tmean, imean, coef, scale, grad_out):
+        _cabi.check(self.lib.mrclip_mpos_backward(d_img.data_ptr(), _DT[d_img.dtype], d_img.stride(0), d_txt.data_ptr(),
+                                                  _DT[d_txt.dtype], d_txt.stride(0), img_rows.data_ptr(), txt_rows.data_ptr(),
+                                                  img_rows.shape[1], img_rows.shape[0], d, cls.data_ptr(), tmean.data_ptr(),
+                                                  imean.data_ptr(), coef, scale.data_ptr(), _ptr(grad_out), self._stream()))
+
+
 _default_engine = None
 
 

@@ -868,34 +868,34 @@ class _MultiPositiveFn(torch.autograd.Function):
             dist.all_gather_into_tensor(labels_all, labels)
         else:
             labels_all = labels
-        # dense class ids in [0, N) without a data-dependent shape (torch.unique would synchronise the host):
-        # sort, flag the first sample of every class, prefix-sum the flags, scatter back
+        # dense class ids in [0, N) without a data-dependent shape (torch.unique would synchronise the host): sort, flag the
+        # first sample of every class, prefix-sum the flags; every class is then a contiguous group of `order`
         sorted_l, order = torch.sort(labels_all)
         first = torch.ones_like(sorted_l)
         first[1:] = (sorted_l[1:] != sorted_l[:-1]).to(sorted_l.dtype)
+        cid_sorted = torch.cumsum(first, 0) - 1                      # class id of every sorted position
         inv_all = torch.empty_like(sorted_l)
-        inv_all[order] = torch.cumsum(first, 0) - 1
-        cnt = torch.zeros((N,), dtype=torch.float32, device=device).index_add_(
-            0, inv_all, torch.ones((N,), dtype=torch.float32, device=device)).clamp_(min=1.0)
-        img_f, txt_f = ws.img_all.float(), ws.txt_all.float()          # the bf16 operands the kernels see
-        t_mean = torch.zeros((N, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, txt_f)
-        i_mean = torch.zeros((N, ws.ld), dtype=torch.float32, device=device).index_add_(0, inv_all, img_f)
-        t_mean /= cnt[:, None]
-        i_mean /= cnt[:, None]
-        inv_r = inv_all[rows]
-        corr_i = txt_f[rows] - t_mean[inv_r]         # T_i - mean_{P(i)} T      [n, ld]
-        corr_t = img_f[rows] - i_mean[inv_r]         # I_j - mean_{P(j)} I
-        pos_img = scale * (img_f[rows] * t_mean[inv_r]).sum(-1)        # (1/c) sum_{P(i)} S_ij
-        pos_txt = scale * (txt_f[rows] * i_mean[inv_r]).sum(-1)
-        ln2 = 0.6931471805599453
-        loss_img = (ws.lse2_row_all[rows] * ln2 - pos_img).mean()
-        loss_txt = (ws.lse2_col_all[rows] * ln2 - pos_txt).mean()
-        loss = torch.empty((), dtype=torch.float32, device=device).copy_(delta * loss_img + (1.0 - delta) * loss_txt)
+        inv_all[order] = cid_sorted                                  # class id of every sample
+        seg_start = torch.full((N,), N, dtype=torch.long, device=device).scatter_reduce_(
+            0, cid_sorted, torch.arange(N, device=device), reduce="amin")
+        seg_cnt = torch.zeros((N,), dtype=torch.long, device=device).index_add_(0, cid_sorted, torch.ones_like(cid_sorted))
+        i32 = torch.int32
+        # class means of the packed (bf16) features the kernels see, one launch per modality (csrc/aux_kernels.cuh)
+        t_mean = torch.empty((N, ws.ld), dtype=torch.float32, device=device)
+        i_mean = torch.empty((N, ws.ld), dtype=torch.float32, device=device)
+        order32, start32, cnt32 = order.to(i32), seg_start.to(i32), seg_cnt.to(i32)
+        eng.class_means(ws.txt_all, order32, start32, cnt32, t_mean)
+        eng.class_means(ws.img_all, order32, start32, cnt32, i_mean)
+        cls_r = inv_all[rows].to(i32).contiguous()
+        # loss = delta * mean_i(lse_row_i - s <I_i, mean_{P(i)} T>) + (1 - delta) * mean_i(lse_col_i - s <T_i, mean_{P(i)} I>)
+        loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
+        eng.mpos_forward(ws.img_all[rows], ws.txt_all[rows], d, cls_r, t_mean, i_mean, ws.lse2_row_all[rows],
+                         ws.lse2_col_all[rows], scale, delta, loss)
 
         ctx.ws, ctx.module, ctx.shape_args = ws, module, (n, N, d, rank, world)
         ctx.lease = module._pool.lease(ws)
         ctx.scale, ctx.delta, ctx.loss_local = scale, float(delta), loss.clone()
-        ctx.corr = (corr_i, corr_t)
+        ctx.cls = (cls_r, t_mean, i_mean)
         ctx.in_dtypes = (image_features.dtype, text_features.dtype)
         ctx.scale_meta = (logit_scale.shape, logit_scale.dtype) if torch.is_tensor(logit_scale) else None
         if not keep_e:
@@ -938,11 +938,9 @@ class _MultiPositiveFn(torch.autograd.Function):
                 work_cs.wait()
                 ent = ms[0].sum() + colsum[rank]
             finish_dt()
-        # class-mean corrections: + s/n * (T_i - mean_{P(i)} T)  and  + s/n * (I_j - mean_{P(j)} I)
-        k = (coef * gout * ctx.scale).to(torch.float32)
-        corr_i, corr_t = ctx.corr
-        d_img += (k * corr_i[:, :d]).to(d_img.dtype)
-        d_txt += (k * corr_t[:, :d]).to(d_txt.dtype)
+        # class-mean corrections: + s/n * (T_i - mean_{P(i)} T)  and  + s/n * (I_j - mean_{P(j)} I), in place
+        cls_r, t_mean, i_mean = ctx.cls
+        eng.mpos_backward(d_img, d_txt, ws.img_all[rows], ws.txt_all[rows], d, cls_r, t_mean, i_mean, coef, ctx.scale, gout)
         d_scale = None
         if need_s:
             # scale * dL/dscale = L + ln2/n * (delta * sum Prow log2 Prow + (1-delta) * sum Pcol log2 Pcol)

@@ -264,6 +264,33 @@ class StandInEngine:
             s = float(scale.item())
             dot_out[0] = float(dot_out[0]) + float((d_out.double() * dot_feat.double()[:, :d_out.shape[1]]).sum() / s)
 
+    # ---- MultiPositiveClipLoss ----------------------------------------------------------------
+    def class_means(self, x_all, order, seg_start, seg_cnt, mean_out):
+        self.calls.append("class_means")
+        mean_out.zero_()
+        xs = x_all.double()
+        for c in range(seg_cnt.shape[0]):
+            k = int(seg_cnt[c])
+            if k > 0:
+                members = order[int(seg_start[c]):int(seg_start[c]) + k].long()
+                mean_out[c] = xs[members].mean(0).float()
+
+    def mpos_forward(self, img_rows, txt_rows, d, cls, tmean, imean, lse2_row, lse2_col, scale, delta, loss):
+        self.calls.append("mpos_forward")
+        s = float(scale.item())
+        c = cls.long()
+        pos_img = s * (img_rows.double() * tmean[c].double()).sum(-1)
+        pos_txt = s * (txt_rows.double() * imean[c].double()).sum(-1)
+        li = delta * (lse2_row.double() / LOG2E - pos_img) + (1.0 - delta) * (lse2_col.double() / LOG2E - pos_txt)
+        loss.view(-1)[0] = float(li.mean())
+
+    def mpos_backward(self, d_img, d_txt, img_rows, txt_rows, d, cls, tmean, imean, coef, scale, grad_out):
+        self.calls.append("mpos_backward")
+        k = coef * float(scale.item()) * (1.0 if grad_out is None else float(grad_out.item()))
+        c = cls.long()
+        d_img += (k * (txt_rows.double() - tmean[c].double()))[:, :d].to(d_img.dtype)
+        d_txt += (k * (img_rows.double() - imean[c].double()))[:, :d].to(d_txt.dtype)
+
     def siglip_fwd_e(self, a_rows, b_all, shape, scale, bias, ws, loss, gmat):
         self.siglip_fwd(a_rows, b_all, shape, scale, bias, ws, loss)
         self.calls[-1] = "siglip_fwd_e"
