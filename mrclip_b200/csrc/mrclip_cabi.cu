@@ -1190,6 +1190,8 @@ constexpr int kMaxBands = 16;
 struct SideStream {
   cudaStream_t st = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr, ev[kMaxBands] = {};
+  cudaStream_t cp[3] = {};          // copy-engine lanes of the text all-gather (several copies in flight)
+  cudaEvent_t cp_join[3] = {};
 };
 SideStream* side_stream() {
   static std::mutex mu;
@@ -1204,6 +1206,9 @@ SideStream* side_stream() {
             cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming) == cudaSuccess &&
             cudaEventCreateWithFlags(&s->join, cudaEventDisableTiming) == cudaSuccess;
   for (int i = 0; ok && i < kMaxBands; ++i) ok = cudaEventCreateWithFlags(&s->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; ok && i < 3; ++i)
+    ok = cudaStreamCreateWithFlags(&s->cp[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&s->cp_join[i], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     delete s;
     s = nullptr;
@@ -1245,33 +1250,43 @@ int push_rows_async(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st) {
   WriteValue32Fn wv = write_value32_fn();
   if (!ss || !wv) return fail(-1, "step: no side stream / stream memory operations");
   CUDA_TRY(cudaEventRecord(ss->fork, st));
-  CUDA_TRY(cudaStreamWaitEvent(ss->st, ss->fork, 0));
   const size_t bytes = (size_t)s->shape.m_rows * s->ld * 2, offset = (size_t)s->shape.label_offset * s->ld * 2;
   const int e = *s->peer.host_epoch;          // already advanced for this step (mrclip_step_forward)
-  ProfScope ps("push_rows(copy engines)", ss->st);
-  for (int k = 1; k < pi.ranks; ++k) {
+  const int lanes = pi.ranks - 1 < 3 ? pi.ranks - 1 : 3;
+  for (int l = 0; l < lanes; ++l) CUDA_TRY(cudaStreamWaitEvent(ss->cp[l], ss->fork, 0));
+  ProfScope ps("push_rows(copy engines)", ss->cp[0]);
+  for (int k = 1; k < pi.ranks; ++k) {        // destination k-1 needs the rows first; three copies in flight
     const int dest = (pi.rank - k + pi.ranks) % pi.ranks;
+    cudaStream_t cs = ss->cp[(k - 1) % lanes];
     CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<void*>(s->peer.txt_peers_host[dest] + offset),
-                             reinterpret_cast<const uint8_t*>(s->txt_all) + offset, bytes, cudaMemcpyDeviceToDevice, ss->st));
-    const CUresult r = wv((CUstream)ss->st,
+                             reinterpret_cast<const uint8_t*>(s->txt_all) + offset, bytes, cudaMemcpyDeviceToDevice, cs));
+    const CUresult r = wv((CUstream)cs,
                           (CUdeviceptr)(s->peer.ctl_block_peers_host[dest] + (size_t)(CH_TEXT * kPeerMaxRanks + pi.rank) * 4),
                           (cuuint32_t)e, 0);
     if (r != CUDA_SUCCESS) return fail(-4, "cuStreamWriteValue32 failed with CUresult %d", (int)r);
   }
-  CUDA_TRY(cudaEventRecord(ss->join, ss->st));
+  for (int l = 0; l < lanes; ++l) CUDA_TRY(cudaEventRecord(ss->cp_join[l], ss->cp[l]));
   return 0;
 }
 // the forward's later kernels (and everything after them) are ordered behind the side-stream push
 int push_rows_join(const mrclip_step* s, const PeerInfo& pi, cudaStream_t st) {
   if (step_overlaps(s, pi)) {
     SideStream* ss = side_stream();
-    if (ss) CUDA_TRY(cudaStreamWaitEvent(st, ss->join, 0));
+    const int lanes = pi.ranks - 1 < 3 ? pi.ranks - 1 : 3;
+    for (int l = 0; ss && l < lanes; ++l) CUDA_TRY(cudaStreamWaitEvent(st, ss->cp_join[l], 0));
   }
   return 0;
 }
 
+// Worth it only when a destination's share is large: below ~4 MB the forward on the local columns is shorter than the
+// copies it would hide (c4 at W=8: 0.48 vs 0.42 ms) and the 2 (W-1) driver calls cost more host time than the step has
+// (c2 at W=8: 0.47 vs 0.31 ms) -- measured, profiles/r2_notes.md.  MRCLIP_AG_OVERLAP_MIN_BYTES overrides.
+size_t ag_overlap_min_bytes() {
+  const char* e = getenv("MRCLIP_AG_OVERLAP_MIN_BYTES");
+  return e ? (size_t)atoll(e) : (size_t)4 << 20;
+}
 bool step_overlaps(const mrclip_step* s, const PeerInfo& pi) {
-  return pi.ranks > 1 && ag_overlap() && s->peer.txt_peers_host && s->peer.ctl_block_peers_host && s->peer.host_epoch &&
+  return pi.ranks > 1 && ag_overlap() && (size_t)s->shape.m_rows * s->ld * 2 >= ag_overlap_min_bytes() && s->peer.txt_peers_host && s->peer.ctl_block_peers_host && s->peer.host_epoch &&
          side_stream() != nullptr && write_value32_fn() != nullptr;
 }
 

@@ -527,13 +527,19 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
             for (int c = 0; c < 64; ++c) a[c] = kMasked;
           }
-          float tmax = a[0];
+          // (four independent chains each: a 64-deep dependent max / add chain is ~250 cycles of pure latency per
+          //  sub-tile with only two epilogue warps per scheduler to hide it)
+          float tm[4] = {a[0], a[1], a[2], a[3]};
 #pragma unroll
-          for (int c = 1; c < 64; ++c) tmax = fmaxf(tmax, a[c]);
+          for (int c = 4; c < 64; c += 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) tm[k] = fmaxf(tm[k], a[c + k]);
+          }
+          const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
           const float wmax = warp_max(tmax);
           const float cw = (Cfg::kRowEnt ? (wmax <= -1e29f) : (wmax == -CUDART_INF_F)) ? 0.f : wmax * sl;
           const float2 sl2 = make_float2(sl, sl), ncw2 = make_float2(-cw, -cw);
-          float2 rs2 = make_float2(0.f, 0.f);
+          float2 rs4[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
           float2 us2 = make_float2(0.f, 0.f);
           float v[64];
 #pragma unroll
@@ -541,9 +547,10 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const float2 t = ffma2(make_float2(a[2 * c], a[2 * c + 1]), sl2, ncw2);
             v[2 * c] = ex2f(t.x);
             v[2 * c + 1] = ex2f(t.y);
-            rs2 = fadd2(rs2, make_float2(v[2 * c], v[2 * c + 1]));
+            rs4[c & 3] = fadd2(rs4[c & 3], make_float2(v[2 * c], v[2 * c + 1]));
             if (Cfg::kRowEnt) us2 = ffma2(make_float2(v[2 * c], v[2 * c + 1]), t, us2);   // sum e * (S2 - cw)
           }
+          const float2 rs2 = fadd2(fadd2(rs4[0], rs4[1]), fadd2(rs4[2], rs4[3]));
           const float rowsum = rs2.x + rs2.y;
           const float mnew = fmaxf(m_run, cw);
           if (Cfg::kRowEnt) {
@@ -567,14 +574,17 @@ tile_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                      make_float4(v[hf * 32 + ck * 4], v[hf * 32 + ck * 4 + 1], v[hf * 32 + ck * 4 + 2],
                                  v[hf * 32 + ck * 4 + 3]));
             __syncwarp();
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};   // four independent chains: the 32 loads stay in flight together
+            float ld[32];                          // all 32 loads issued before the first add consumes one
 #pragma unroll
             for (int r8 = 0; r8 < 8; ++r8) {
               const uint32_t base = stg + r8 * 128 + ((((lane >> 2) ^ r8)) << 4) + (lane & 3) * 4;
 #pragma unroll
-              for (int r = 0; r < 4; ++r) acc[r] += __uint_as_float(lds_u32(base + r * 1024));
+              for (int r = 0; r < 4; ++r) ld[r8 * 4 + r] = __uint_as_float(lds_u32(base + r * 1024));
             }
-            cs[hf] = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+            float acc[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[k] = (ld[k] + ld[k + 8]) + (ld[k + 16] + ld[k + 24]);
+            cs[hf] = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
           }
           store_e(v);   // bf16 E through the same staging tile (its __syncwarp orders it after the column reads)
           const int band = rb * 4 + q;
