@@ -1113,7 +1113,7 @@ PeerInfo make_peer(const mrclip_step* s) {
   return pi;
 }
 
-int check_step(const mrclip_step* s) {
+int check_step(const mrclip_step* s, bool backward) {
   if (!s) return fail(-1, "step: NULL descriptor");
   if (int e = check_shape(s->shape, s->ld)) return e;
   const int ranks = s->peer.ranks > 1 ? s->peer.ranks : 1;
@@ -1125,7 +1125,8 @@ int check_step(const mrclip_step* s) {
     const mrclip_peer& p = s->peer;
     if (ranks > kPeerMaxRanks) return fail(-1, "step: at most %d ranks", kPeerMaxRanks);
     if (p.rank < 0 || p.rank >= ranks || s->shape.label_offset != p.rank * s->shape.m_rows) return fail(-1, "step: bad rank / label_offset");
-    if (!p.ctl_block_peers || !p.ctl_block || !p.ctl || !p.txt_peers || !p.recv_peers || !p.recv || (s->kind == 0 && !p.stats_peers))
+    if (!p.ctl_block_peers || !p.ctl_block || !p.ctl || !p.txt_peers || (backward && (!p.recv_peers || !p.recv)) ||
+        (s->kind == 0 && !p.stats_peers))
       return fail(-1, "step: NULL peer buffer");
     if (!gemm_pairs()) return fail(-1, "step: the multi-rank step needs the CTA-pair GEMM (unset MRCLIP_GEMM_CTA)");
   }
@@ -1346,7 +1347,7 @@ int mrclip_step_uses_fwd_ds(const mrclip_step* s) {
 int mrclip_step_forward(const mrclip_step* s, const void* img, int img_dtype, long img_ld, const void* txt, int txt_dtype,
                         long txt_ld, const float* scale, const float* bias, int need_grad, int raw, float* loss_out,
                         void* stream) {
-  if (int e = check_step(s)) return e;
+  if (int e = check_step(s, false)) return e;
   if (!img || !txt || !scale || !loss_out) return fail(-1, "step_forward: NULL argument");
   if (need_grad && !s->emat) return fail(-1, "step_forward: need_grad without an E block");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1449,7 +1450,7 @@ int mrclip_normalize_bwd(const void* y, long y_ld, const float* inv_norm, int ro
 int mrclip_step_backward(const mrclip_step* s, const float* scale, const float* grad_out, float coef, void* d_img,
                          int d_img_dtype, long d_img_ld, void* d_txt, int d_txt_dtype, long d_txt_ld, float* d_scale,
                          float* d_bias, void* stream) {
-  if (int e = check_step(s)) return e;
+  if (int e = check_step(s, true)) return e;
   if (!scale || !d_img || !d_txt || !s->emat) return fail(-1, "step_backward: NULL argument");
   if (d_img_dtype < 0 || d_img_dtype > 2 || d_txt_dtype < 0 || d_txt_dtype > 2) return fail(-1, "step_backward: bad output dtype");
   cudaStream_t st = (cudaStream_t)stream;

@@ -4,6 +4,8 @@ Pins oracle/clip_oracle.py against every vector oracle/gen_golden.py recorded fr
 reference (all four (local_loss, gather_with_grad) modes at W=2/4/8, W=1, GradScaler-style
 grad_output, ragged sizes, SigLIP at W=1/3/4).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -145,3 +147,22 @@ def test_multipositive_oracle_matches_reference(name):
         assert rel_err(out[r]["d_image"], ref["d_image"]) <= GRAD_TOL
         assert rel_err(out[r]["d_text"], ref["d_text"]) <= GRAD_TOL
         assert abs(out[r]["d_logit_scale"] - float(ref["d_scale"])) <= 5e-5 * max(abs(float(ref["d_scale"])), 1e-3)
+
+
+def test_ref_copy_is_unmodified():
+    """oracle/_ref (what bench.py's reference arm and experiments/train_step.py run on the GPU box) is a byte-for-byte
+    copy of the reference sources: every file matches the sha256 in its manifest and, where /root/reference exists,
+    the original."""
+    import hashlib
+    import json
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref")
+    manifest_path = os.path.join(root, "MANIFEST.json")
+    if not os.path.exists(manifest_path):
+        pytest.skip("oracle/_ref has not been made on this machine (python oracle/make_ref.py)")
+    manifest = json.load(open(manifest_path))
+    assert "open_clip/loss.py" in manifest and "open_clip_train/train.py" in manifest
+    for rel, meta in manifest.items():
+        data = open(os.path.join(root, "src", rel), "rb").read()
+        assert hashlib.sha256(data).hexdigest() == meta["sha256"], rel
+        if os.path.exists(meta["source"]):
+            assert open(meta["source"], "rb").read() == data, rel
