@@ -122,7 +122,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cuda.matmul.allow_tf32 = False
     names = [a for a in sys.argv[1:] if not a.startswith("-")] or list(CASES)
-    transports = ["push", "nccl"] if world > 1 else ["local"]
+    # push: peer memory, copy-engine all-gather for shares >= 4 MB; push-ce: the same with the copy engines forced on
+    # every shape (small cases only); nccl: NCCL collectives through the Python orchestration
+    transports = ["push", "push-ce", "nccl"] if world > 1 else ["local"]
     failures = 0
     for name in names:
         c = CASES[name]
@@ -155,7 +157,10 @@ def main():
         for mode in modes:
             ref = None
             for tr in transports:
+                if tr == "push-ce" and N > 8192:
+                    continue
                 os.environ["MRCLIP_RS"] = os.environ["MRCLIP_AG"] = ("nccl" if tr == "nccl" else "push")
+                os.environ["MRCLIP_AG_OVERLAP_MIN_BYTES"] = "0" if tr == "push-ce" else str(4 << 20)
                 i = img[rows].clone().requires_grad_(True)
                 t = txt[rows].clone().requires_grad_(True)
                 s = torch.tensor(c["scale"], device=dev, requires_grad=True)
@@ -182,6 +187,10 @@ def main():
                         ref = torch_ref.mpos_reference(img[rows], txt[rows], c["scale"], lab[rows], c["delta"], rank, world, go)
                     labels_ok = True
                 (loss * go).backward()
+                if c["kind"] == "clip" and not raw:       # evaluation: the no-grad forward (no E block) gives the same loss
+                    with torch.no_grad():
+                        if abs(float(mod(i, t, s)) - float(loss)) > 1e-5 * abs(float(loss)):
+                            labels_ok = False
                 ours = dict(loss=loss.detach(), d_image=i.grad, d_text=t.grad, d_scale=s.grad)
                 if c["kind"] == "siglip":
                     ours["d_bias"] = b.grad
@@ -198,7 +207,7 @@ def main():
                     print(f"MISMATCH rank {rank} {name} {mode} {tr}: {bad} {errs}", flush=True)
                 if rank == 0:
                     tag = f"{name} W={world} N={N} D={D}" + (f" (ll={int(mode[0])},gg={int(mode[1])})" if c["kind"] == "clip" else "")
-                    print(f"{tag:44s} {tr:5s} loss={float(ours['loss']):.6f} worst over ranks: loss={vals[0]:.2e} dI={vals[1]:.2e} "
+                    print(f"{tag:44s} {tr:7s} loss={float(ours['loss']):.6f} worst over ranks: loss={vals[0]:.2e} dI={vals[1]:.2e} "
                           f"dT={vals[2]:.2e} ds={vals[3]:.2e}" + (f" db={vals[4]:.2e}" if c["kind"] == "siglip" else "") +
                           f" labels={'exact' if labels_ok else 'WRONG'}  [{'ok' if vals[-1].item() == 0 else 'FAIL'}]", flush=True)
             del ref
