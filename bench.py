@@ -1,12 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- ClipLoss fwd+bwd pairs/sec at global batch 32768, dim 768 (BASELINE.json config 3).
+"""bench.py -- ClipLoss fwd+bwd pairs/sec at global batch 32768, dim 768 (BASELINE.json configs[2]).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (port)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own loss module on the host cores
+    python bench.py --config c1|c2|c4                        # the other BASELINE configs (same JSON line)
 
-N>1 is launched by torchrun (one rank per GPU, NCCL).  One "step" is one forward+backward of
-``ClipLoss(local_loss=True, gather_with_grad=True)`` over the rank's share of the global batch,
-through the public module (``mrclip_b200.ClipLoss``), collectives included.  Prints ONE JSON line.
+N>1 is launched by torchrun (one rank per GPU).  One "step" is one forward+backward of
+``ClipLoss(local_loss=True, gather_with_grad=True)`` over the rank's share of the global batch, through the public
+module (``mrclip_b200.ClipLoss``), exchanges included.  Before anything is timed the same step is checked against the
+reference's fp32 torch graph evaluated on the GPU (``parity`` in the line; a failing check aborts the run).  ``value`` is
+device-timed with the inputs resident; ``e2e`` times the module call with pinned host buffers (copies inside the region);
+``roofline`` is the costliest launch group, timed by the library's own events in a pass of the same length;
+``cpu_baseline`` / ``--impl reference`` run the unmodified reference file from ``oracle/_ref`` (``oracle/ref_runner.py``).
+Prints ONE JSON line.
 """
 import argparse
 import json
