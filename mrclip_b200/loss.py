@@ -1,24 +1,30 @@
-"""Drop-in ``ClipLoss`` / ``SigLipLoss`` / ``gather_features`` for MR-CLIP on B200.
+"""Drop-in ``ClipLoss`` / ``SigLipLoss`` / ``MultiPositiveClipLoss`` / ``gather_features`` for MR-CLIP on B200.
 
 Same constructor and call signatures as the reference (``src/open_clip/loss.py``:
-``gather_features`` :21-65, ``ClipLoss`` :68-139, ``SigLipLoss`` :314-448), so
-``open_clip.factory.create_loss`` (factory.py:432-503) and ``train_one_epoch`` (train.py:128)
-use it unchanged.  Behind the signatures the N x N logit matrix never exists: the forward runs the
-tcgen05 tile kernel with a fused online log-sum-exp (``csrc/tile_kernel.cuh``) and keeps only the bf16
-exponentials E of this rank's row block; the backward rescales E into the gradient of the logits in one
-HBM pass and contracts it twice with plain tcgen05 GEMMs (``csrc/gemm_kernel.cuh``): three N x N x D
-contractions per step, the algorithmic minimum ("emat" backend).  The older backends (``MRCLIP_BWD=gmat``:
-recompute S and write G, 4-5 contractions; ``fused``: O(N*D) memory, 7) remain selectable and tested.
+``gather_features`` :21-65, ``ClipLoss`` :68-139, ``SigLipLoss`` :314-448, ``MultiPositiveClipLoss`` :671-747), so
+``open_clip.factory.create_loss`` (factory.py:432-503) and ``train_one_epoch`` (train.py:128) use it unchanged.  Behind
+the signatures the N x N logit matrix never exists: the forward runs the tcgen05 tile kernel with a fused online
+log-sum-exp (``csrc/tile_kernel.cuh``) and keeps only the bf16 exponentials E of this rank's row block; the backward
+rescales E into the gradient of the logits in one HBM pass and contracts it twice with plain tcgen05 GEMMs
+(``csrc/gemm2_kernel.cuh``): three N x N x D contractions per step, the algorithmic minimum ("emat" backend).  The older
+backends (``MRCLIP_BWD=gmat``: recompute S and write G, 4-5 contractions; ``fused``: O(N*D) memory, 7) remain selectable
+and tested.
 
-Multi-rank decomposition (one process per GPU, ``torch.distributed`` / NCCL for plumbing only):
-rank r owns rows [r*n, (r+1)*n) of both modalities.  Forward: all-gather of the bf16-packed
-features, row-block tiles -> exact row LSE + per-column partial (max,sum) -> one small all-gather
-of those statistics.  Backward (emat): dI_r = G_r . T_all is complete on its rank; the text gradient is
-the sum over ranks of G_q^T . I_q, i.e. one reduce-scatter of [N, D] fp32 partials that runs while the
-dI GEMM computes -- it replaces the reference's reduce-scatter of W full copies per modality
-(torch/distributed/nn/functional.py:343-347).  (gmat / fused backends: a second row pass T_r vs I_all
-instead, no gradient collective.)  The per-rank values reproduce the reference's conventions exactly
-(SURVEY.md §3a):
+Two orchestrations of the same kernels:
+
+* default -- ``mrclip_step_forward`` / ``mrclip_step_backward`` (``mrclip_b200/step.py``, ``csrc/mrclip_cabi.cu``): one C call
+  per direction.  On several ranks (one process per GPU) nothing but the library's kernels and the copy engines move
+  data, over NVLink peer memory mapped by torch symmetric memory, ordered by device-side flags (``csrc/peer_sync.cuh``):
+  no NCCL call and no barrier inside a step.
+* ``MRCLIP_STEP=py``, NCCL transports, the gmat / fused backends, ``(local_loss, not gather_with_grad)``, the
+  multi-positive loss and the CPU tests (stand-in engine, gloo): the per-kernel sequence written out below in Python.
+
+Multi-rank decomposition: rank r owns rows [r*n, (r+1)*n) of both modalities.  Forward: all-gather of the bf16-packed
+TEXT rows (the image rows of other ranks are never needed), row-block tiles -> exact row LSE + per-column partial
+(max, sum) -> exchange of those statistics.  Backward: dI_r = G_r . T_all is complete on its rank; the text gradient is
+the sum over ranks of G_q^T . I_q, i.e. one reduce-scatter of [N, D] partials fused into the GEMM that produces them -- it
+replaces the reference's reduce-scatter of W full copies per modality (torch/distributed/nn/functional.py:343-347).
+The per-rank values reproduce the reference's conventions exactly:
 
   (local_loss, gather_with_grad)   loss on rank r     d features                d logit_scale
   (F, F)                           L_global           1/(2N) * (Pr + Pc - 2d)   global
@@ -26,7 +32,9 @@ instead, no gradient collective.)  The per-rank values reproduce the reference's
   (T, F)                           L_r                1/(2n) * (P_own - d)      local
   (T, T)                           L_r                1/(2n) * (Pr + Pc - 2d)   local
 
-There is no CPU path: tensors must live on an sm_100a device, otherwise the call raises.
+There is no CPU path: tensors must live on one sm_100a device, otherwise the call raises.  ``logit_scale`` must be
+positive (it is ``exp(.)`` in the reference, model.py:324): the forward takes its sub-tile references on the unscaled
+accumulators.
 """
 from __future__ import annotations
 
@@ -383,7 +391,9 @@ def _rows_major(x):
     return x if x.stride(1) == 1 else x.contiguous()
 
 
-def _scalar_f32(x, device):
+def _scalar_f32(x, device, positive=False):
+    if positive and not torch.is_tensor(x) and float(x) <= 0.0:
+        raise ValueError(f"logit_scale must be positive, got {x}")
     if torch.is_tensor(x):
         return x.detach().reshape(-1)[:1].to(device=device, dtype=torch.float32).contiguous()
     return torch.tensor([float(x)], dtype=torch.float32, device=device)
@@ -581,7 +591,7 @@ class _ClipLossFn(torch.autograd.Function):
         world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
         ws = module._pool.take(eng, device, n, world, d)
         N = ws.N
-        scale = _scalar_f32(logit_scale, device)
+        scale = _scalar_f32(logit_scale, device, positive=not raw)
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
 
@@ -856,7 +866,7 @@ class _MultiPositiveFn(torch.autograd.Function):
             raise NotImplementedError("MultiPositiveClipLoss: per-rank batch must be >= 8 and world_size <= 64")
         ws = module._pool.take(eng, device, n, world, d)
         N = ws.N
-        scale = _scalar_f32(logit_scale, device)
+        scale = _scalar_f32(logit_scale, device, positive=True)
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
         keep_e = any(ctx.needs_input_grad)
@@ -982,7 +992,7 @@ class _SigLipLossFn(torch.autograd.Function):
         world, rank = (module.world_size, module.rank) if module.world_size > 1 else (1, 0)
         ws = module._pool.take(eng, device, n, world, d)
         N = ws.N
-        scale = _scalar_f32(logit_scale, device)
+        scale = _scalar_f32(logit_scale, device, positive=not raw)
         bias = _scalar_f32(logit_bias, device) if logit_bias is not None else None
         shape = Shape(n, N, d, rank * n)
         rows = slice(rank * n, (rank + 1) * n)
