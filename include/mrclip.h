@@ -266,6 +266,10 @@ typedef struct mrclip_step {
 
 size_t mrclip_peer_block_bytes(void);
 size_t mrclip_step_small_floats(void);
+/* sizeof(mrclip_step) / sizeof(mrclip_peer) as this library was compiled: lets a foreign-language binding check its
+ * struct declarations against the ABI at load time (tests/test_cabi.py does so for the ctypes ones). */
+size_t mrclip_step_struct_bytes(void);
+size_t mrclip_peer_struct_bytes(void);
 /* 1 when mrclip_step_backward will take d logit_scale from forward-side row sums (the forward must then be told:
  * fwd_ds), 0 when it uses the entropy sums of the rescale pass.  Pure function of the shape and mode. */
 int mrclip_step_uses_fwd_ds(const mrclip_step* s);

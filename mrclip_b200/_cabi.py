@@ -61,6 +61,8 @@ SIGNATURES = {
     "mrclip_sum_slots_bf16": (_I, [_P, _I, _I, _I, _P, _I, _L, _P, _L, _P, _P]),
     "mrclip_peer_block_bytes": (C.c_size_t, []),
     "mrclip_step_small_floats": (C.c_size_t, []),
+    "mrclip_step_struct_bytes": (C.c_size_t, []),
+    "mrclip_peer_struct_bytes": (C.c_size_t, []),
     "mrclip_step_uses_fwd_ds": (_I, [_P]),
     "mrclip_step_forward": (_I, [_P, _P, _I, _L, _P, _I, _L, _P, _P, _I, _I, _P, _P]),
     "mrclip_normalize_bwd": (_I, [_P, _L, _P, _I, _I, _P, _I, _L, _P]),

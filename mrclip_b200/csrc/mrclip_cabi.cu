@@ -1335,6 +1335,8 @@ int mrclip_prof_report(char* buf, size_t cap) {
 }
 
 size_t mrclip_peer_block_bytes(void) { return kPeerBlockBytes; }
+size_t mrclip_step_struct_bytes(void) { return sizeof(mrclip_step); }
+size_t mrclip_peer_struct_bytes(void) { return sizeof(mrclip_peer); }
 size_t mrclip_step_small_floats(void) { return kSmallFloats; }
 
 int mrclip_step_uses_fwd_ds(const mrclip_step* s) {

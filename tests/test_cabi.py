@@ -59,3 +59,27 @@ def test_product_refuses_to_run_without_gpu():
     x = torch.nn.functional.normalize(torch.randn(8, 16), dim=-1)
     with pytest.raises(RuntimeError, match="no CPU (fallback|path)"):
         loss(x.requires_grad_(True), x.clone(), torch.tensor(10.0))
+
+
+def test_step_descriptor_structs_match_the_library():
+    """The ctypes twins of mrclip_step / mrclip_peer (mrclip_b200/step.py) have the size the library was compiled with,
+    the step entries reject a NULL / inconsistent descriptor with an error code (no crash, no compute on CPU), and the
+    pure planning entry answers without a GPU."""
+    from mrclip_b200.step import Peer, Step
+    lib = _cabi.load()
+    assert ctypes.sizeof(Step) == lib.mrclip_step_struct_bytes()
+    assert ctypes.sizeof(Peer) == lib.mrclip_peer_struct_bytes()
+    assert lib.mrclip_peer_block_bytes() == 4096 and lib.mrclip_step_small_floats() >= 128 + 64 * 64
+    assert lib.mrclip_step_forward(None, None, 0, 0, None, 0, 0, None, None, 0, 0, None, None) < 0
+    assert b"NULL descriptor" in lib.mrclip_last_error()
+    st = Step()
+    st.shape = _cabi.Shape(4096, 32768, 768, 3 * 4096)
+    st.ld, st.kind, st.local_loss = 768, 0, 1
+    st.peer = Peer(8, 3, None, None, None, None, None, None, None, 1, None, None, None)
+    assert lib.mrclip_step_uses_fwd_ds(ctypes.byref(st)) == 1          # large multi-rank local loss: forward-side d scale
+    st.local_loss = 0
+    assert lib.mrclip_step_uses_fwd_ds(ctypes.byref(st)) == 0          # global loss: entropy sums
+    st.local_loss, st.shape = 1, _cabi.Shape(512, 4096, 512, 3 * 512)
+    assert lib.mrclip_step_uses_fwd_ds(ctypes.byref(st)) == 0          # n*N < 2^22
+    st.shape = _cabi.Shape(4096, 32768, 768, 0)                        # label_offset must be rank * n
+    assert lib.mrclip_step_backward(ctypes.byref(st), None, None, 0.0, None, 0, 0, None, 0, 0, None, None, None) < 0
