@@ -40,7 +40,6 @@ from __future__ import annotations
 
 import functools
 import os
-import weakref
 from typing import Optional
 
 import torch
@@ -56,6 +55,7 @@ except ImportError:  # pragma: no cover
 
 from ._cabi import Shape
 from .engine import default_engine
+from .step import KIND_CLIP, KIND_SIGLIP
 from .exchange import (NeighbourExchange, NeighbourExchangeBidir, neighbour_exchange,  # noqa: F401  (reference names)
                        neighbour_exchange_bidir, neighbour_exchange_bidir_with_grad, neighbour_exchange_with_grad)
 
@@ -606,7 +606,7 @@ class _ClipLossFn(torch.autograd.Function):
         if (not split_g or not need_grad) and _step_path_ok(eng, ws, world, need_grad):
             # one C call launches the whole forward (csrc/mrclip_cabi.cu: mrclip_step_forward); on several ranks the text
             # all-gather rides on NVLink peer stores and overlaps the tiles on this rank's own columns
-            plan = ws.step_plan(eng, 0, module.local_loss or world == 1, rank)
+            plan = ws.step_plan(eng, KIND_CLIP, module.local_loss or world == 1, rank)
             if world > 1:
                 ws.flip ^= 1
             loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
@@ -1000,7 +1000,7 @@ class _SigLipLossFn(torch.autograd.Function):
         loss = torch.empty((), dtype=torch.float32, device=device)   # 0-d, not a view: callers may modify it in place
         ctx.fast = None
         if _step_path_ok(eng, ws, world, any(ctx.needs_input_grad)):
-            plan = ws.step_plan(eng, 1, True, rank)
+            plan = ws.step_plan(eng, KIND_SIGLIP, True, rank)
             if world > 1:
                 ws.flip ^= 1
             plan.forward(eng, ws.flip if world > 1 else 0, _rows_major(image_features), _rows_major(text_features), scale,
