@@ -20,9 +20,8 @@ import torch
 
 from . import _cabi
 from ._cabi import Shape
-from .engine import default_engine
 
-__all__ = ["get_clip_metrics", "rank_statistics"]
+__all__ = ["get_clip_metrics", "rank_statistics", "positive_layout"]
 
 
 def _dense_classes(labels):
@@ -32,24 +31,34 @@ def _dense_classes(labels):
     return np.asarray(ids, dtype=np.int64)
 
 
+def positive_layout(class_ids):
+    """Host-side layout of the positive lists for ``class_ids`` (ints, one per sample, shared by rows and columns).
+    Returns (cls int64 [N], m int64 [N] = positives per row incl. the row's own column, ordinal int64 [N] = position of
+    sample j inside its class, off int64 [N] = start of row i's list, total = sum(m)): column j of class c lands in slot
+    off[i] + ordinal[j] of every row i of class c, so each list is filled exactly once without atomics."""
+    cls = np.asarray(class_ids, dtype=np.int64)
+    n = cls.shape[0]
+    sizes = np.bincount(cls)
+    m = sizes[cls]
+    order = np.argsort(cls, kind="stable")
+    ordinal = np.empty(n, dtype=np.int64)
+    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
+    ordinal[order] = np.arange(n) - starts[cls[order]]
+    off = np.concatenate(([0], np.cumsum(m)[:-1])).astype(np.int64)
+    return cls, m, ordinal, off, int(m.sum())
+
+
 def rank_statistics(row_features, col_features, class_ids):
     """For every row: (best, mean) = 0-based rank of its best positive and mean 0-based rank of all its positives among the
     columns, ``class_ids`` (int array [N], shared by rows and columns) defining the positives.  Returns two float64 numpy
     arrays of length N.  Everything N x N runs in ``tile_kernel<MODE_RANK>``."""
+    from .engine import default_engine
     eng = default_engine()
     lib = eng.lib
     dev = row_features.device
     n, d = row_features.shape
     assert col_features.shape == (n, d) and len(class_ids) == n
-    cls = np.asarray(class_ids, dtype=np.int64)
-    sizes = np.bincount(cls)
-    m = sizes[cls]                                            # positives per row (the row's own column included)
-    order = np.argsort(cls, kind="stable")
-    ordinal = np.empty(n, dtype=np.int64)                      # position of sample j inside its class
-    starts = np.concatenate(([0], np.cumsum(sizes)[:-1]))
-    ordinal[order] = np.arange(n) - starts[cls[order]]
-    off = np.concatenate(([0], np.cumsum(m)[:-1])).astype(np.int64)
-    total = int(m.sum())
+    cls, m, ordinal, off, total = positive_layout(class_ids)
     ld, npad = eng.padded_dim(d), eng.padded_cols(n)
     a = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)
     b = torch.zeros((n, ld), dtype=torch.bfloat16, device=dev)

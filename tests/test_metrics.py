@@ -115,3 +115,19 @@ def test_gpu_rank_statistics_large(n, d, classes):
     mean_ref = ((pairs_ref + m * (m - 1) / 2) / m).cpu().numpy()
     assert abs(mean.mean() - mean_ref.mean()) <= 1e-4 * mean_ref.mean()
     assert np.abs(mean - mean_ref).max() <= 1e-3 * max(mean_ref.max(), 1.0) + 1.0
+
+
+def test_positive_layout_fills_every_list_exactly_once():
+    """Host side of the rank epilogue: slot off[i] + ordinal[j] over the columns j of row i's class is a bijection onto
+    row i's list [off[i], off[i] + m[i]), and the lists tile [0, total) without gaps or overlaps."""
+    from mrclip_b200.metrics import positive_layout
+    rng = np.random.default_rng(0)
+    for n, classes in ((1, 1), (17, 1), (64, 64), (300, 7), (257, 40)):
+        ids = rng.integers(0, classes, size=n) if classes < n else rng.permutation(n)
+        cls, m, ordinal, off, total = positive_layout(ids)
+        assert total == int(sum(np.bincount(cls) ** 2)) and off[0] == 0
+        assert np.array_equal(off[1:], np.cumsum(m)[:-1])
+        for i in range(n):
+            cols = np.nonzero(cls == cls[i])[0]
+            assert m[i] == cols.size
+            assert sorted(off[i] + ordinal[cols]) == list(range(off[i], off[i] + m[i]))
