@@ -452,3 +452,26 @@ def test_cpu_tensors_raise_without_engine_override():
     i, t = _feat()
     with pytest.raises(RuntimeError, match="no CPU path"):
         ClipLoss()(i, t, torch.tensor(10.0))
+
+
+# ---- feature hand-off (forward_raw) on the CPU path: exactly the reference composition -------------------------------
+def test_forward_raw_falls_back_to_the_reference_composition(standin_engine):
+    """Without the whole-step path (stand-in engine) forward_raw is forward(F.normalize(i), F.normalize(t), exp(log_scale))
+    -- model.py:282-301, :324 in front of loss.py:128-139 -- with gradients reaching the raw rows and the log-scale."""
+    import torch_ref
+    g = torch.Generator().manual_seed(5)
+    raw_i = (torch.randn(24, 16, generator=g) * 3).requires_grad_(True)
+    raw_t = (torch.randn(24, 16, generator=g) * 0.2).requires_grad_(True)
+    ls = torch.tensor(2.0, requires_grad=True)
+    out = ClipLoss().forward_raw(raw_i, raw_t, ls, output_dict=True)
+    assert list(out) == ["contrastive_loss"]
+    out["contrastive_loss"].backward()
+    ref = torch_ref.clip_reference(raw_i, raw_t, 2.0, raw=True)
+    assert abs(float(out["contrastive_loss"]) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
+    assert rel_err(raw_i.grad.numpy(), ref["d_image"].numpy()) <= 1e-2        # (features rounded to bf16 by the engine)
+    assert rel_err(raw_t.grad.numpy(), ref["d_text"].numpy()) <= 1e-2
+    assert abs(float(ls.grad) - float(ref["d_scale"])) <= 1e-2 * abs(float(ref["d_scale"]))
+    b = torch.tensor(-3.0, requires_grad=True)
+    loss = SigLipLoss().forward_raw(raw_i.detach(), raw_t.detach(), ls.detach(), b)
+    ref = torch_ref.siglip_reference(raw_i, raw_t, 2.0, -3.0, raw=True)
+    assert abs(float(loss) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
