@@ -475,3 +475,29 @@ def test_forward_raw_falls_back_to_the_reference_composition(standin_engine):
     loss = SigLipLoss().forward_raw(raw_i.detach(), raw_t.detach(), ls.detach(), b)
     ref = torch_ref.siglip_reference(raw_i, raw_t, 2.0, -3.0, raw=True)
     assert abs(float(loss) - float(ref["loss"])) <= 2e-3 * abs(float(ref["loss"]))
+
+
+# ---- the peer-memory / NCCL choice is made by all ranks together ------------------------------------
+def _agree_worker(rank, world, init_file, ret):
+    dist.init_process_group("gloo", init_method=f"file://{init_file}", rank=rank, world_size=world)
+    try:
+        from mrclip_b200.loss import _all_ranks_ok, _symmetric_alloc
+        dev = torch.device("cpu")
+        res = [_all_ranks_ok(True, dev), _all_ranks_ok(rank != 1, dev)]          # one rank fails -> nobody proceeds
+        # a module whose world_size is not the default group's must not build peer tables on that group
+        res.append(_symmetric_alloc([((4,), torch.float32)], dev, world + 1, "test") is None)
+        ret[rank] = res
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_symmetric_memory_decision_is_collective():
+    import warnings
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    with tempfile.TemporaryDirectory() as td, warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        mp.spawn(_agree_worker, args=(3, os.path.join(td, "init"), ret), nprocs=3, join=True)
+    for r in range(3):
+        assert ret[r] == [True, False, True]
